@@ -1,0 +1,61 @@
+// ws_common.cuh — shared device-side definitions for the wavespec kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ws {
+
+constexpr int kMaxTopK = 32;
+constexpr int kRowFields = 15;
+
+// Everything a kernel needs to process one batch of equally long series.
+struct Params {
+    const double* series;      // [n_series][series_len], device
+    int64_t series_stride;     // elements between series
+    int32_t n_series;
+    int32_t series_len;
+    int32_t N;                 // window length (power of two)
+    int32_t log2N;
+    int32_t hop;
+    int32_t K;                 // top_k
+    int32_t row_stride;
+    int64_t nwin;              // windows per series (also the per-series stride of every output plane)
+    int64_t win_offset;        // first window this launch covers
+    int64_t chunk_nwin;        // number of windows this launch covers (feed plane holds exactly these)
+    int32_t band_lo, band_hi;  // inclusive bin band, already clipped; lo > hi means empty
+    int32_t detrend;           // WAVESPEC_DETREND_*
+    int32_t has_window;        // window table present
+    int32_t select;            // WAVESPEC_SELECT_*
+    double iir_alpha, iir_c;   // trend IIR coefficients (A2a)
+    double sample_rate_seconds;
+    const double2* tw;         // exp(-2 pi i m / N), m = 0..N-1
+    const double* wtab;        // window coefficients w[i], i = 0..N-1 (or nullptr)
+    const double* apow;        // iir_alpha^j, j = 0..N-1 (or nullptr)
+    const double* feed;        // optional pre-built per-window feed [n_series][nwin][N] (PLA), or nullptr
+    double* spectra;           // [n_series][nwin][N] interleaved, or nullptr
+    double* rows;              // [n_series][nwin][K][row_stride], or nullptr
+    int32_t* bins;             // [n_series][nwin][K], or nullptr
+    double* waves;             // [n_series][nwin][K] A8a, or nullptr
+    double* contrib;           // [n_series][nwin][K] A8b (input of the weight-Kalman scan), or nullptr
+    double* phase;             // [n_series][nwin][3][N/2], or nullptr
+    int32_t tile_windows;      // windows per CTA tile
+};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+
+// 64-bit warp shuffles
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// (power, bin) ordering used by every top-K rule of the reference: larger power first; on equal
+// power the candidate met first in the ascending bin scan stays ahead (strict '>' insertion,
+// Legacy/WaveSpecZZ_1.0.3-pla-kalman-fast-gpuopt-nodetrend.mq5:546-553).  NaN never wins.
+__device__ __forceinline__ bool better(double p, int pos, double bp, int bpos) {
+    return (p > bp) || (p == bp && pos < bpos);
+}
+
+}  // namespace ws

@@ -1,0 +1,179 @@
+// ws_series.cu — per-series sequential recursions, one series per thread across the batch.
+// Compiled with -fmad=false: every add/mul/div/sqrt is a separately rounded IEEE operation in
+// the reference's evaluation order, so given identical inputs the results are bit-identical to
+// the CPU statement.
+//
+//  * Kalman4D  : ResetKalmanState / StepKalman4D,
+//                Legacy/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:2015-2125 (defaults :885-901),
+//                driven as in the bar loop :3354-3360 (reset on the first processed bar, then
+//                step that same bar).  State = 4 + 16 doubles carried across bars.
+//  * weight-Kalman blend : UpdateKalman, Legacy/WaveSpecZZ_1.0.4-kalman.mq5:194-231
+//                (= UpdateKalmanWave, Legacy/WaveSpecZZ_1.0.4-old.mq5:2606-2649).
+#include "ws_common.cuh"
+#include "ws_series.h"
+
+namespace ws {
+
+__global__ void kalman4d_kernel(const double* __restrict__ z_base, int64_t series_stride,
+                                int64_t z_step, int32_t n_series, int64_t nwin,
+                                const KalmanParams kp, double* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_series) return;
+    const double* z = z_base + (int64_t)s * series_stride;
+    double* o = out + (int64_t)s * nwin;
+
+    const double q_scale = fmax(0.05, kp.follow_strength);
+    const double Qp = fmax(1e-9, kp.q_pos * q_scale);
+    const double Qv = fmax(1e-9, kp.q_vel * q_scale);
+    const double Qa = fmax(1e-9, kp.q_acc * q_scale);
+    const double Qj = fmax(1e-9, kp.q_jerk * q_scale);
+    const double R = fmax(1e-9, kp.meas_noise);
+    const double c16 = 1.0 / 6.0, c112 = 1.0 / 12.0, c136 = 1.0 / 36.0;
+
+    double pos = 0, vel = 0, acc = 0, jerk = 0;
+    double P00 = 0, P01 = 0, P02 = 0, P03 = 0, P10 = 0, P11 = 0, P12 = 0, P13 = 0;
+    double P20 = 0, P21 = 0, P22 = 0, P23 = 0, P30 = 0, P31 = 0, P32 = 0, P33 = 0;
+    double ema_prev = 0.0;
+    bool ema_ready = false;
+
+    for (int64_t w = 0; w < nwin; w++) {
+        const double zz = z[w * z_step];
+        if (w == 0) {   // ResetKalmanState(first measurement)
+            pos = zz; vel = kp.init_vel; acc = kp.init_acc; jerk = kp.init_jerk;
+            P00 = fmax(1e-9, kp.init_var_pos); P11 = fmax(1e-9, kp.init_var_vel);
+            P22 = fmax(1e-9, kp.init_var_acc); P33 = fmax(1e-9, kp.init_var_jerk);
+            P01 = P02 = P03 = P10 = P12 = P13 = P20 = P21 = P23 = P30 = P31 = P32 = 0.0;
+            ema_ready = false;
+        }
+        double x0p = pos + vel + 0.5 * acc + c16 * jerk;
+        double x1p = vel + acc + 0.5 * jerk;
+        double x2p = acc + jerk;
+        double x3p = jerk;
+
+        double P00p = P00 + P01 + 0.5 * P02 + c16 * P03
+                    + P10 + P11 + 0.5 * P12 + c16 * P13
+                    + 0.5 * P20 + 0.5 * P21 + 0.25 * P22 + c112 * P23
+                    + c16 * P30 + c16 * P31 + c112 * P32 + c136 * P33
+                    + Qp;
+        double P01p = P01 + P02 + 0.5 * P03 + P11 + P12 + 0.5 * P13 + 0.5 * P21 + 0.5 * P22 + 0.25 * P23 + c16 * P31 + c16 * P32 + c112 * P33;
+        double P02p = P02 + P03 + P12 + P13 + 0.5 * P22 + 0.5 * P23 + c16 * P32 + c16 * P33;
+        double P03p = P03 + P13 + 0.5 * P23 + c16 * P33;
+        double P11p = P11 + 2.0 * P12 + P13 + P21 + 2.0 * P22 + P23 + 0.5 * P31 + 0.5 * P32 + 0.25 * P33 + Qv;
+        double P12p = P12 + P13 + P22 + P23 + 0.5 * P32 + 0.5 * P33;
+        double P13p = P13 + P23 + 0.5 * P33;
+        double P22p = P22 + 2.0 * P23 + P33 + Qa;
+        double P23p = P23 + P33;
+        double P33p = P33 + Qj;
+        double P10p = P01p, P20p = P02p, P30p = P03p;
+        double P21p = P12p, P31p = P13p, P32p = P23p;
+
+        double y = zz - x0p;
+        double S = P00p + R;
+        if (kp.adapt_gain > 0.0) {
+            double sigma = sqrt(S);
+            double k = fmin(5.0, fabs(y) / sigma) * kp.adapt_gain;
+            double boost = 1.0 + k;
+            P00p += (boost - 1.0) * Qp;
+            P11p += (boost - 1.0) * Qv;
+            P22p += (boost - 1.0) * Qa;
+            P33p += (boost - 1.0) * Qj;
+            S = P00p + R;
+        }
+        if (kp.clip_std > 0.0) {
+            double sigma = sqrt(S);
+            double lim = kp.clip_std * sigma;
+            if (y > lim) y = lim;
+            if (y < -lim) y = -lim;
+        }
+        double K0 = P00p / S, K1 = P10p / S, K2 = P20p / S, K3 = P30p / S;
+
+        pos = x0p + K0 * y;
+        vel = x1p + K1 * y;
+        acc = x2p + K2 * y;
+        jerk = x3p + K3 * y;
+
+        double P00n = (1.0 - K0) * P00p, P01n = (1.0 - K0) * P01p, P02n = (1.0 - K0) * P02p, P03n = (1.0 - K0) * P03p;
+        double P10n = P10p - K1 * P00p, P11n = P11p - K1 * P01p, P12n = P12p - K1 * P02p, P13n = P13p - K1 * P03p;
+        double P20n = P20p - K2 * P00p, P21n = P21p - K2 * P01p, P22n = P22p - K2 * P02p, P23n = P23p - K2 * P03p;
+        double P30n = P30p - K3 * P00p, P31n = P31p - K3 * P01p, P32n = P32p - K3 * P02p, P33n = P33p - K3 * P03p;
+
+        P00 = fmax(1e-12, P00n); P01 = P01n; P02 = P02n; P03 = P03n;
+        P10 = P10n; P11 = fmax(1e-12, P11n); P12 = P12n; P13 = P13n;
+        P20 = P20n; P21 = P21n; P22 = fmax(1e-12, P22n); P23 = P23n;
+        P30 = P30n; P31 = P31n; P32 = P32n; P33 = fmax(1e-12, P33n);
+
+        double outv = pos;
+        if (kp.ema_blend_period > 0.0) {
+            double alpha = 2.0 / (kp.ema_blend_period + 1.0);
+            if (!ema_ready) { ema_prev = outv; ema_ready = true; }
+            ema_prev = alpha * outv + (1.0 - alpha) * ema_prev;
+            outv = ema_prev;
+        }
+        o[w] = outv;
+    }
+}
+
+__global__ void wkalman_kernel(const double* __restrict__ contrib, const int32_t* __restrict__ bins,
+                               const double* __restrict__ meas_base, int64_t series_stride,
+                               int64_t meas_step, int32_t n_series, int64_t nwin, int32_t K,
+                               double q, double r, double p0, double* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_series) return;
+    const double Q = fmax(1e-9, q), R = fmax(1e-9, r);
+    double wgt[kMaxTopK], cov[kMaxTopK];
+    for (int i = 0; i < kMaxTopK; i++) { wgt[i] = 0.0; cov[i] = fmax(1e-6, p0); }
+    const double* meas = meas_base + (int64_t)s * series_stride;
+    for (int64_t w = 0; w < nwin; w++) {
+        const double* cv = contrib + ((int64_t)s * nwin + w) * K;
+        const int32_t* bn = bins + ((int64_t)s * nwin + w) * K;
+        double vals[kMaxTopK];
+        int use = 0;
+        for (int k = 0; k < K; k++) if (bn[k] >= 0) vals[use++] = cv[k];
+        double blended = 0.0;
+        if (use > 0) {
+            double residual = meas[w * meas_step];
+            double innovation = R;
+            double cov_tmp[kMaxTopK], w_tmp[kMaxTopK];
+            for (int i = 0; i < use; i++) {
+                cov[i] += Q;
+                cov_tmp[i] = cov[i];
+                w_tmp[i] = wgt[i];
+                residual -= vals[i] * w_tmp[i];
+                innovation += vals[i] * vals[i] * cov_tmp[i];
+            }
+            if (innovation < 1e-9) innovation = R;
+            for (int i = 0; i < use; i++) {
+                const double H = vals[i];
+                const double c = cov_tmp[i];
+                const double Kg = (c * H) / innovation;
+                const double nw = w_tmp[i] + Kg * residual;
+                const double nc = (1.0 - Kg * H) * c;
+                wgt[i] = nw;
+                cov[i] = fmax(nc, 1e-9);
+                blended += nw * H;
+            }
+        }
+        out[(int64_t)s * nwin + w] = blended;
+    }
+}
+
+cudaError_t launch_kalman4d(const double* z_base, int64_t series_stride, int64_t z_step,
+                            int32_t n_series, int64_t nwin, const KalmanParams& kp, double* out,
+                            cudaStream_t stream) {
+    const int threads = 32;
+    const int blocks = (n_series + threads - 1) / threads;
+    kalman4d_kernel<<<blocks, threads, 0, stream>>>(z_base, series_stride, z_step, n_series, nwin, kp, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wkalman(const double* contrib, const int32_t* bins, const double* meas_base,
+                           int64_t series_stride, int64_t meas_step, int32_t n_series, int64_t nwin,
+                           int32_t K, double q, double r, double p0, double* out, cudaStream_t stream) {
+    const int threads = 32;
+    const int blocks = (n_series + threads - 1) / threads;
+    wkalman_kernel<<<blocks, threads, 0, stream>>>(contrib, bins, meas_base, series_stride, meas_step,
+                                                   n_series, nwin, K, q, r, p0, out);
+    return cudaGetLastError();
+}
+
+}  // namespace ws

@@ -1,0 +1,42 @@
+// ws_series.h — host-visible declarations of the kernel launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ws_common.cuh"
+
+namespace ws {
+
+// Same field order as wavespec_kalman4d_params (include/wavespec_abi.h).
+struct KalmanParams {
+    double follow_strength, q_pos, q_vel, q_acc, q_jerk, adapt_gain, meas_noise;
+    double init_var_pos, init_var_vel, init_var_acc, init_var_jerk;
+    double init_vel, init_acc, init_jerk, clip_std, ema_blend_period;
+};
+
+// ws_window_fft.cu
+cudaError_t launch_window_fft(Params p, cudaStream_t stream);
+
+// ws_sliding.cu
+bool sliding_shared_supported(const Params& p);
+cudaError_t launch_sliding_shared(Params p, cudaStream_t stream);
+
+// ws_series.cu
+cudaError_t launch_kalman4d(const double* z_base, int64_t series_stride, int64_t z_step,
+                            int32_t n_series, int64_t nwin, const KalmanParams& kp, double* out,
+                            cudaStream_t stream);
+cudaError_t launch_wkalman(const double* contrib, const int32_t* bins, const double* meas_base,
+                           int64_t series_stride, int64_t meas_step, int32_t n_series, int64_t nwin,
+                           int32_t K, double q, double r, double p0, double* out, cudaStream_t stream);
+
+// ws_pla.cu
+cudaError_t launch_pla(const double* series, int64_t series_stride, int32_t n_series, int64_t nwin,
+                       int32_t N, int32_t hop, int32_t max_segments, double max_error, double* lines,
+                       int32_t* seg_bounds, int32_t* seg_counts, int32_t bounds_cap,
+                       cudaStream_t stream);
+
+// ws_inverse.cu
+cudaError_t launch_inverse_real(const double* d_spec, int32_t N, int32_t n_windows, const double2* tw,
+                                double* d_out, cudaStream_t stream);
+
+}  // namespace ws

@@ -1,0 +1,367 @@
+// ws_window_fft.cu — generic per-window real FFT with fused prologue and epilogue (sm_100a).
+//
+// Used whenever a window needs its own transform: any detrend / window function / PLA feed
+// (SURVEY.md section 8a rows A2a, A2b, A3, A11), hop > 1, single-window calls
+// (gpu_fft_real_forward, gpu_extract_cycles) and contiguous batches.  The plain hop-1
+// rectangular case is served by the shared-butterfly kernel in ws_sliding.cu instead.
+//
+// One CTA owns a tile of consecutive windows of one series.  The tile's samples are staged in
+// shared memory once (each sample is read from HBM once per tile, not once per window).  Each
+// window becomes an N/2-point complex Stockham FFT (radix-4 passes + one radix-2 pass when
+// log2(N/2) is odd) of z[m] = v[2m] + i v[2m+1] held in shared memory, followed by the
+// real-input split, the power spectrum and a warp-per-window top-K epilogue.
+//
+// The transform uses exact table twiddles, not the reference's multiplicative recurrence
+// (Legacy/WaveSpecZZ_1.0.2.mq5:955-970): results agree to ~1e-14 relative, inside the 1e-9 bar.
+#include "ws_common.cuh"
+#include "ws_epilogue.cuh"
+
+namespace ws {
+
+constexpr int kThreads = 128;
+
+// prologue value of sample n of a window starting at tile offset `off`
+struct Prologue {
+    const double* tile;     // shared: x (or x - y for the IIR detrend)
+    const double* wtab;     // global window table or nullptr
+    const double* apow;     // global alpha^j or nullptr
+    double sub;             // mean (DETREND_MEAN) or delta_w (DETREND_IIR)
+    int mode;
+    __device__ __forceinline__ double operator()(int off, int n) const {
+        double v = tile[off + n];
+        if (mode == 2) v = v - sub;
+        else if (mode == 1) v = v - __ldg(apow + n) * sub;
+        if (wtab) v = v * __ldg(wtab + n);
+        return v;
+    }
+};
+
+__device__ __forceinline__ void r4_butterfly(double2& a0, double2& a1, double2& a2, double2& a3) {
+    double2 b0 = cadd(a0, a2), b1 = csub(a0, a2), b2 = cadd(a1, a3);
+    double2 d = csub(a1, a3);
+    double2 b3 = make_double2(d.y, -d.x);   // -i * (a1 - a3)
+    a0 = cadd(b0, b2); a2 = csub(b0, b2); a1 = cadd(b1, b3); a3 = csub(b1, b3);
+}
+
+// Trend IIR of Legacy/...-kalman-fast.mq5:3367-3379 over x[0..L): y[0] = c (x0 + x0),
+// y[a] = c (x[a] + x[a-1]) + alpha y[a-1].  Blocked over the CTA: local recurrences from zero,
+// a serial carry pass over the kThreads chunk ends, then the alpha^k fix-up.  Differs from the
+// serial loop by rounding only (a few ulp of y).
+__device__ void cta_trend_iir(const double* x, int L, double al, double c, double* y, double* carry) {
+    const int tid = threadIdx.x;
+    const int chunk = (L + kThreads - 1) / kThreads;
+    const int a0 = tid * chunk;
+    double acc = 0.0;
+    for (int a = a0; a < a0 + chunk && a < L; a++) {
+        double u = (a == 0) ? c * (x[0] + x[0]) : c * (x[a] + x[a - 1]);
+        acc = u + al * acc;
+        y[a] = acc;
+    }
+    carry[tid] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double ac = pow(al, (double)chunk);
+        double run = 0.0;
+        for (int t = 0; t < kThreads; t++) {
+            double e = carry[t];
+            carry[t] = run;                 // carry-in of chunk t
+            run = e + ac * run;
+        }
+    }
+    __syncthreads();
+    double cin = carry[tid];
+    double f = al;
+    for (int a = a0; a < a0 + chunk && a < L; a++) { y[a] = y[a] + f * cin; f *= al; }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads)
+window_fft_kernel(const Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = p.N, M = N >> 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = p.tile_windows;
+    const int64_t w0 = p.win_offset + (int64_t)blockIdx.x * T;
+    const int s = blockIdx.y;
+    const int64_t nwin = p.nwin;
+    const int64_t wend = p.win_offset + p.chunk_nwin;
+    const int tw_count = (int)((w0 + T <= wend) ? T : (wend - w0));
+    if (tw_count <= 0) return;
+    const int Lt = (tw_count - 1) * p.hop + N;
+
+    // windows processed concurrently by the CTA: as many as keep every thread on one radix-4
+    // butterfly per pass (M/4 butterflies per window)
+    const int q = M >> 2;                          // butterflies per window per radix-4 pass
+    int wpc = q > 0 ? kThreads / q : kThreads;     // N >= 8
+    if (wpc < 1) wpc = 1;
+    if (wpc > 4) wpc = 4;
+
+    // shared layout: tile[Lt_max] | delta[T] | bufA[wpc*M] | bufB[wpc*M] | ord[wpc*M] ints
+    const bool from_feed = p.feed != nullptr;
+    const int Lt_max = from_feed ? wpc * N : (T - 1) * p.hop + N;
+    double* tile = reinterpret_cast<double*>(smem_raw);
+    double* delta = tile + ((Lt_max + 1) & ~1);
+    double2* bufA = reinterpret_cast<double2*>(delta + ((T + 1) & ~1));
+    double2* bufB = bufA + (size_t)wpc * M;
+    int* ord = reinterpret_cast<int*>(bufB + (size_t)wpc * M);
+    double* scr = reinterpret_cast<double*>(ord + (((size_t)wpc * M + 1) & ~(size_t)1));  // IIR scratch
+
+    const int pro_mode = (from_feed && p.detrend == 1) ? 0 : p.detrend;
+    const double* src = p.series + (int64_t)s * p.series_stride + w0 * p.hop;
+
+    if (!from_feed) {
+        for (int i = tid; i < Lt; i += kThreads) tile[i] = src[i];
+        __syncthreads();
+        if (p.detrend == 1) {
+            // Trend IIR (Legacy/...-kalman-fast.mq5:3367-3379) restarted per window:
+            //   tr_w[j] = y[w+j] + alpha^j * (2c x[w] - y[w])
+            // for ANY y obeying y[a] = c (x[a] + x[a-1]) + alpha y[a-1] on the tile, so y is run
+            // once per tile (blocked: local recurrences, serial carry pass, fix-up) and each
+            // window only needs delta_w = 2c x[w] - y[w].
+            double* y = scr;
+            double* carry = y + Lt_max;
+            const double c = p.iir_c;
+            cta_trend_iir(tile, Lt, p.iir_alpha, c, y, carry);
+            for (int t = tid; t < tw_count; t += kThreads) {
+                int a = t * p.hop;
+                delta[t] = c * (tile[a] + tile[a]) - y[a];
+            }
+            __syncthreads();
+            for (int i = tid; i < Lt; i += kThreads) tile[i] = tile[i] - y[i];
+            __syncthreads();
+        }
+    }
+
+    const int log2M = p.log2N - 1;
+    const bool odd = (log2M & 1) != 0;
+
+    for (int wb = 0; wb < tw_count; wb += wpc) {
+        const int nw = (tw_count - wb) < wpc ? (tw_count - wb) : wpc;
+
+        if (from_feed) {
+            // pre-built feed (PLA lines): one window per row, no overlap to exploit
+            for (int i = tid; i < nw * N; i += kThreads) {
+                int wl = i / N, n = i - wl * N;
+                tile[wl * N + n] = p.feed[((int64_t)s * p.chunk_nwin + (w0 - p.win_offset) + wb + wl) * N + n];
+            }
+            __syncthreads();
+            if (p.detrend == 1) {
+                // per-window restart on a pre-built feed: no tile-level sharing possible
+                double* y = scr;
+                double* carry = y + Lt_max;
+                for (int wl = 0; wl < nw; wl++) {
+                    cta_trend_iir(tile + wl * N, N, p.iir_alpha, p.iir_c, y, carry);
+                    for (int i = tid; i < N; i += kThreads) tile[wl * N + i] = tile[wl * N + i] - y[i];
+                    __syncthreads();
+                }
+            }
+        }
+        if (p.detrend == 2) {
+            // mean removal (Legacy/WaveSpecZZ_gpu_wip.mq5:940-943); one warp per window
+            for (int wl = warp; wl < nw; wl += kThreads / 32) {
+                int off = from_feed ? wl * N : (wb + wl) * p.hop;
+                double sum = 0.0;
+                for (int n = lane; n < N; n += 32) sum += tile[off + n];
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) sum += shfl_xor_d(sum, m);
+                if (lane == 0) delta[wb + wl] = sum / (double)N;
+            }
+            __syncthreads();
+        }
+
+        // ---- pass 0 (Ns = 1): straight from the staged samples through the prologue
+        double2* in = bufA;
+        double2* out = bufB;
+        if (M >= 4) {
+            for (int idx = tid; idx < nw * q; idx += kThreads) {
+                int wl = idx / q, j = idx - wl * q;
+                int off = from_feed ? wl * N : (wb + wl) * p.hop;
+                Prologue pr{tile, p.has_window ? p.wtab : nullptr, p.apow,
+                            pro_mode ? delta[wb + wl] : 0.0, pro_mode};
+                double2 a[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    int m = j + r * q;
+                    a[r] = make_double2(pr(off, 2 * m), pr(off, 2 * m + 1));
+                }
+                r4_butterfly(a[0], a[1], a[2], a[3]);
+                double2* o = out + (size_t)wl * M + 4 * j;
+                o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = a[3];
+            }
+        } else {
+            // M = 1 or 2 (N = 2, 4): copy through the prologue; the radix-2 tail finishes it
+            for (int idx = tid; idx < nw * M; idx += kThreads) {
+                int wl = idx / M, m = idx - wl * M;
+                int off = from_feed ? wl * N : (wb + wl) * p.hop;
+                Prologue pr{tile, p.has_window ? p.wtab : nullptr, p.apow,
+                            pro_mode ? delta[wb + wl] : 0.0, pro_mode};
+                out[(size_t)wl * M + m] = make_double2(pr(off, 2 * m), pr(off, 2 * m + 1));
+            }
+        }
+        __syncthreads();
+        { double2* t = in; in = out; out = t; }
+
+        // ---- remaining radix-4 passes
+        int Ns = (M >= 4) ? 4 : 1;
+        for (; Ns * 4 <= M; Ns <<= 2) {
+            const int tstep = N / (4 * Ns);
+            for (int idx = tid; idx < nw * q; idx += kThreads) {
+                int wl = idx / q, j = idx - wl * q;
+                const double2* iw = in + (size_t)wl * M;
+                int k = j & (Ns - 1);
+                double2 a0 = iw[j], a1 = iw[j + q], a2 = iw[j + 2 * q], a3 = iw[j + 3 * q];
+                int t = tstep * k;
+                a1 = cmul(a1, __ldg(p.tw + t));
+                a2 = cmul(a2, __ldg(p.tw + 2 * t));
+                a3 = cmul(a3, __ldg(p.tw + 3 * t));
+                r4_butterfly(a0, a1, a2, a3);
+                double2* o = out + (size_t)wl * M + ((j - k) << 2) + k;
+                o[0] = a0; o[Ns] = a1; o[2 * Ns] = a2; o[3 * Ns] = a3;
+            }
+            __syncthreads();
+            double2* t = in; in = out; out = t;
+        }
+        // ---- radix-2 tail when log2(M) is odd (or M == 2)
+        if ((odd && M >= 2) || M == 2) {
+            const int h = M >> 1;
+            for (int idx = tid; idx < nw * h; idx += kThreads) {
+                int wl = idx / h, j = idx - wl * h;
+                const double2* iw = in + (size_t)wl * M;
+                double2 a0 = iw[j];
+                double2 a1 = cmul(iw[j + h], __ldg(p.tw + 2 * j));
+                double2* o = out + (size_t)wl * M;
+                o[j] = cadd(a0, a1); o[j + h] = csub(a0, a1);
+            }
+            __syncthreads();
+            double2* t = in; in = out; out = t;
+        }
+
+        // ---- real-input split: X[k] = E + W_N^k O ; power ; spectra store
+        // `in` holds Z; X goes to `out`, powers reuse the (dead) Z buffer afterwards.
+        for (int idx = tid; idx < nw * M; idx += kThreads) {
+            int wl = idx / M, k = idx - wl * M;
+            const double2* Z = in + (size_t)wl * M;
+            double2 zk = Z[k];
+            double2 zm = cconj(Z[(M - k) & (M - 1)]);
+            double2 E = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y + zm.y));
+            double2 D = csub(zk, zm);
+            double2 O = make_double2(0.5 * D.y, -0.5 * D.x);       // -i/2 * D
+            double2 X = cadd(E, cmul(__ldg(p.tw + k), O));
+            out[(size_t)wl * M + k] = X;
+            if (p.spectra) {
+                double2* g = reinterpret_cast<double2*>(
+                    p.spectra + (((int64_t)s * nwin + w0 + wb + wl)) * N);
+                g[k] = X;
+            }
+        }
+        __syncthreads();
+        double* pw = reinterpret_cast<double*>(in);    // Z is dead: wpc*M double2 = room for M doubles per window
+        for (int idx = tid; idx < nw * M; idx += kThreads) {
+            int wl = idx / M, k = idx - wl * M;
+            double2 X = out[(size_t)wl * M + k];
+            pw[(size_t)wl * M + k] = X.x * X.x + X.y * X.y;
+        }
+        __syncthreads();
+
+        const bool want_sel = p.bins || p.rows || p.waves || p.contrib;
+        if (want_sel) {
+            for (int wl = warp; wl < nw; wl += kThreads / 32)
+                warp_select_emit(p, pw + (size_t)wl * M, out + (size_t)wl * M, ord + (size_t)wl * M,
+                                 (int64_t)s * nwin + w0 + wb + wl);
+        }
+        if (p.phase) {
+            // A6 phase chain (Legacy/...-kalman-fast.mq5:1183-1263) over bins 0..M-1.
+            // phase: parallel atan2; unwrap: serial prefix per window (one lane), as the
+            // reference accumulates it; group delay: parallel differences.
+            double* ph = pw;                      // overwrite powers (selection is done below the barrier)
+            __syncthreads();
+            for (int idx = tid; idx < nw * M; idx += kThreads) {
+                int wl = idx / M, k = idx - wl * M;
+                double2 X = out[(size_t)wl * M + k];
+                ph[(size_t)wl * M + k] = atan2(X.y, X.x);
+            }
+            __syncthreads();
+            double* un = reinterpret_cast<double*>(out);    // X is dead after atan2
+            for (int wl = tid; wl < nw; wl += kThreads) {
+                const double* f = ph + (size_t)wl * M;
+                double* u = un + (size_t)wl * M;
+                u[0] = f[0];
+                for (int i = 1; i < M; i++) {
+                    double diff = f[i] - f[i - 1];
+                    double corr = 0.0;
+                    if (diff > kPi) corr = -2.0 * kPi;
+                    else if (diff < -kPi) corr = 2.0 * kPi;
+                    u[i] = u[i - 1] + diff + corr;
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < nw * M; idx += kThreads) {
+                int wl = idx / M, k = idx - wl * M;
+                const double* u = un + (size_t)wl * M;
+                double g;
+                if (M < 3) g = 0.0;
+                else if (k == 0) g = -(u[1] - u[0]);
+                else if (k == M - 1) g = -(u[M - 1] - u[M - 2]);
+                else g = -(u[k + 1] - u[k - 1]) / 2.0;
+                if (g > 100.0) g = 100.0;
+                if (g < -100.0) g = -100.0;
+                double* o = p.phase + (((int64_t)s * nwin + w0 + wb + wl)) * (int64_t)(3 * M);
+                o[k] = ph[(size_t)wl * M + k];
+                o[M + k] = u[k];
+                o[2 * M + k] = g;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Host-side launcher.  Returns the dynamic shared memory it used (0 on error).
+size_t window_fft_smem_bytes(const Params& p, int tile_windows) {
+    const int N = p.N, M = N / 2;
+    int q = M / 4;
+    int wpc = q > 0 ? kThreads / q : kThreads;
+    if (wpc < 1) wpc = 1;
+    if (wpc > 4) wpc = 4;
+    size_t Lt = p.feed ? (size_t)wpc * N : (size_t)(tile_windows - 1) * p.hop + N;
+    size_t doubles = ((Lt + 1) & ~(size_t)1) + ((tile_windows + 1) & ~1);
+    size_t bytes = doubles * 8 + 2 * (size_t)wpc * M * 16 + (((size_t)wpc * M + 1) & ~(size_t)1) * 4;
+    if (p.detrend == 1) bytes += (Lt + kThreads) * 8;
+    return bytes;
+}
+
+int window_fft_pick_tile(const Params& p) {
+    // tile sized so that the staged samples stay near 16 KB and, for the IIR detrend, fit the
+    // scratch carved out of bufA (Lt <= 2*wpc*M doubles)
+    const int N = p.N, M = N / 2;
+    int q = M / 4;
+    int wpc = q > 0 ? kThreads / q : kThreads;
+    if (wpc < 1) wpc = 1;
+    if (wpc > 4) wpc = 4;
+    if (p.feed) return wpc;
+    long budget = 4096 > N + 63 ? 4096 : N + 63;  // doubles
+    long t = (budget - N) / p.hop + 1;
+    if (t < 1) t = 1;
+    if (t > 64) t = 64;
+    if (p.chunk_nwin < t) t = (long)p.chunk_nwin;
+    // keep tiles a multiple of wpc so no iteration runs half empty
+    if (t > wpc) t -= t % wpc;
+    return (int)t;
+}
+
+cudaError_t launch_window_fft(Params p, cudaStream_t stream) {
+    p.tile_windows = window_fft_pick_tile(p);
+    size_t smem = window_fft_smem_bytes(p, p.tile_windows);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(window_fft_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    dim3 grid((unsigned)((p.chunk_nwin + p.tile_windows - 1) / p.tile_windows), (unsigned)p.n_series);
+    window_fft_kernel<<<grid, kThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace ws

@@ -1,0 +1,399 @@
+"""GPU parity tests: libwavespec.so (through the C ABI, host buffers) against the CPU oracle on
+the same seeded inputs.
+
+Bars (north_star): selected cycle bins and PLA pivot indices bit-exact; spectra and
+reconstructed waves within 1e-9 relative (max |dX| / max |X| per window)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from fft_wavespec_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def br():
+    from fft_wavespec_b200 import bridge
+    st = bridge.gpu_init(0, 8)
+    assert st == bridge.OK, bridge.last_error()
+    yield bridge
+    bridge.gpu_shutdown()
+
+
+def rel_err(got, ref):
+    """max |got-ref| / max |ref| per window (last axis)."""
+    den = np.abs(ref).max(axis=-1)
+    den = np.where(den == 0, 1.0, den)
+    return (np.abs(got - ref).max(axis=-1) / den).max()
+
+
+def near_ties(spectra, lo, hi, k, gap=1e-11):
+    """count windows whose k-th/(k+1)-th in-band powers are closer than `gap` relative."""
+    p = spectra[:, 0::2] ** 2 + spectra[:, 1::2] ** 2
+    band = np.sort(p[:, lo:hi + 1], axis=1)[:, ::-1]
+    if band.shape[1] <= k:
+        return 0
+    a, b = band[:, k - 1], band[:, k]
+    return int(np.sum(np.abs(a - b) <= gap * np.maximum(a, 1e-300)))
+
+
+def ocfg_from(oracle, cfg):
+    o = oracle.PipelineCfg()
+    C.memmove(C.byref(o), C.byref(cfg), C.sizeof(o))
+    return o
+
+
+# ---- A4: forward FFT behind gpu_fft_real_forward (imports.mqh:8) --------------------------------
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 64, 256, 512, 1024, 2048, 4096, 8192, 16384])
+def test_fft_real_forward_matches_oracle(br, oracle, n):
+    x = synth.random_walk(100 + n, n)
+    out = br.gpu_fft_real_forward(x)
+    ref = oracle.fft_interleaved(x)
+    assert np.abs(out - ref).max() / np.abs(ref).max() < REL_TOL
+    # detrended-like input (no large DC): per-bin accuracy is visible here
+    y = np.random.default_rng(n).standard_normal(n)
+    out = br.gpu_fft_real_forward(y)
+    ref = oracle.fft_interleaved(y)
+    assert np.abs(out - ref).max() / np.abs(ref).max() < 1e-13
+
+
+def test_fft_known_answers(br):
+    n, k = 1024, 37
+    t = np.arange(n)
+    out = br.gpu_fft_real_forward(2.5 * np.cos(2 * np.pi * k * t / n + 0.3))
+    p = out[0::2] ** 2 + out[1::2] ** 2
+    assert int(np.argmax(p)) == k and p[k] == pytest.approx((2.5 * n / 2) ** 2, rel=1e-12)
+    flat = br.gpu_fft_real_forward(np.full(n, 1.23456))
+    assert np.all(flat[2:] == 0.0)                      # exact zeros off DC, like the CPU statement
+    imp = np.zeros(n); imp[0] = 3.0
+    assert np.allclose(br.gpu_fft_real_forward(imp)[0::2], 3.0)
+
+
+def test_fft_bad_args(br):
+    with pytest.raises(br.WaveSpecError) as e:
+        br.gpu_fft_real_forward(np.zeros(1000))
+    assert e.value.status == br.BAD_ARGS
+    with pytest.raises(br.WaveSpecError):
+        br.gpu_fft_real_forward(np.zeros(1))
+    assert "power of two" in br.last_error()
+
+
+def test_fft_batch_and_sliding(br, oracle):
+    n, nwin = 256, 7
+    x = synth.random_walk(5, n * nwin)
+    out = br.gpu_fft_real_forward_batch(x, n, nwin)
+    for w in range(nwin):
+        ref = oracle.fft_interleaved(x[w * n:(w + 1) * n])
+        assert np.abs(out[w] - ref).max() / np.abs(ref).max() < REL_TOL
+    for hop in (1, 3, 64):
+        sl = br.fft_real_forward_sliding(x[:900], n, hop)
+        assert sl.shape[0] == 1 + (900 - n) // hop
+        for w in (0, sl.shape[0] // 2, sl.shape[0] - 1):
+            ref = oracle.fft_interleaved(x[w * hop:w * hop + n])
+            assert np.abs(sl[w] - ref).max() / np.abs(ref).max() < REL_TOL
+
+
+def test_fft_inverse_roundtrip(br):
+    for n in (4, 64, 1024, 4096):
+        x = np.random.default_rng(n).standard_normal(n)
+        spec = br.gpu_fft_real_forward(x)
+        back = br.gpu_fft_real_inverse(spec)
+        nyq = np.sum(x * (-1.0) ** np.arange(n))          # the dropped Nyquist bin
+        expect = x - nyq * (-1.0) ** np.arange(n) / n
+        assert np.abs(back - expect).max() < 1e-12
+
+
+# ---- the five BASELINE configs at oracle-sized lengths ------------------------------------------
+def run_both(br, oracle, series, cfg, outputs):
+    got = br.pipeline_host(series, cfg, outputs)
+    ref = oracle.pipeline_series(series, ocfg_from(oracle, cfg), outputs)
+    return got, ref
+
+
+def check_planes(br, got, ref, cfg):
+    n = cfg.window_len
+    if "spectra" in ref:
+        assert rel_err(got["spectra"], ref["spectra"]) < REL_TOL
+    if "bins" in ref:
+        assert np.array_equal(got["bins"], ref["bins"]), "selected cycle bins differ"
+    if "waves" in ref:
+        scale = np.abs(ref["waves"]).max()
+        assert np.abs(got["waves"] - ref["waves"]).max() <= REL_TOL * scale
+    if "rows" in ref:
+        g, r = got["rows"], ref["rows"]
+        for f in (0, 1, 2, 6, 14):                          # amplitude, freq, period, energy, method
+            assert np.abs(g[..., f] - r[..., f]).max() <= REL_TOL * max(1e-300, np.abs(r[..., f]).max())
+        # phase compared on the circle, eta modulo half a period
+        dph = np.angle(np.exp(1j * (g[..., 3] - r[..., 3])))
+        assert np.abs(dph).max() < 1e-7
+        m = min(cfg.row_stride, 15)
+        if m > 4:
+            half = 0.5 * np.where(r[..., 2] > 0, r[..., 2], 1.0)
+            d = np.abs(g[..., 4] - r[..., 4])
+            d = np.minimum(d, np.abs(half - d))
+            assert d.max() < 1e-5
+    if "kalman" in ref:
+        assert np.array_equal(got["kalman"], ref["kalman"]), "Kalman4D must be bit-identical"
+    if "wkalman" in ref:
+        assert np.abs(got["wkalman"] - ref["wkalman"]).max() <= 1e-9 * max(1.0, np.abs(ref["wkalman"]).max())
+    if "phase" in ref:
+        gp, rp = got["phase"], ref["phase"]
+        dph = np.angle(np.exp(1j * (gp[:, 0] - rp[:, 0])))
+        assert np.abs(dph).max() < 1e-6
+
+
+def test_config1_mean_hann_top5(br, oracle):
+    """C1: N=512, mean removal + Hann (gpu_wip form), top-5, band 9-200."""
+    s = synth.random_walk(0, 4000)
+    cfg = br.default_cfg(512, top_k=5, min_period=9.0, max_period=200.0, detrend=br.DETREND_MEAN,
+                         window_type=br.WINDOW_HANN_WIP)
+    out = br.OUT_SPECTRA | br.OUT_BINS | br.OUT_ROWS | br.OUT_WAVES
+    got, ref = run_both(br, oracle, s, cfg, out)
+    check_planes(br, got, ref, cfg)
+    assert near_ties(ref["spectra"], 3, 56, 5) == 0
+
+
+def test_config2_plain_top8(br, oracle):
+    """C2: N=1024, no detrend / window, top-8, band 18-200 (nodetrend.mq5 path)."""
+    s = synth.random_walk_batch(0, 3, 3500)
+    cfg = br.default_cfg(1024, top_k=8, min_period=18.0, max_period=200.0)
+    out = br.OUT_SPECTRA | br.OUT_BINS | br.OUT_ROWS | br.OUT_WAVES
+    got = br.pipeline_host(s, cfg, out)
+    for i in range(3):
+        ref = oracle.pipeline_series(s[i], ocfg_from(oracle, cfg), out)
+        check_planes(br, {k: v[i] for k, v in got.items()}, ref, cfg)
+        # per-bin check off DC: relative to the in-band magnitudes, not the DC term
+        gb = got["spectra"][i][:, 12:114]; rb = ref["spectra"][:, 12:114]
+        assert rel_err(gb, rb) < REL_TOL
+
+
+def test_config3_iir_blackman_kalman(br, oracle):
+    """C3: N=2048, trend IIR T=1024, Blackman, Kalman4D, band 18-52."""
+    s = synth.random_walk(2, 2048 + 700)
+    cfg = br.default_cfg(2048, top_k=8, min_period=18.0, max_period=52.0, detrend=br.DETREND_IIR,
+                         trend_period=1024.0, window_type=br.WINDOW_BLACKMAN)
+    out = br.OUT_SPECTRA | br.OUT_BINS | br.OUT_KALMAN | br.OUT_WAVES
+    got, ref = run_both(br, oracle, s, cfg, out)
+    check_planes(br, got, ref, cfg)
+    gb = got["spectra"][:, 80:228]; rb = ref["spectra"][:, 80:228]     # the band itself
+    assert rel_err(gb, rb) < REL_TOL
+
+
+def test_config4_phase_and_top8_reconstruction(br, oracle):
+    """C4: N=1024, phase chain + A8a/A8b outputs for the top-8 cycles; Hann + selection sort +
+    weight-Kalman as in WaveSpecZZ_1.0.4-kalman.mq5."""
+    s = synth.random_walk(3, 1024 + 500)
+    cfg = br.default_cfg(1024, top_k=8, min_period=12.0, max_period=256.0, window_type=br.WINDOW_HANN,
+                         select=br.SELECT_SORT)
+    out = br.OUT_SPECTRA | br.OUT_BINS | br.OUT_WAVES | br.OUT_ROWS | br.OUT_WKALMAN | br.OUT_PHASE
+    got, ref = run_both(br, oracle, s, cfg, out)
+    check_planes(br, got, ref, cfg)
+    # unwrapped phase / group delay only where no bin sits within 1e-6 of a +-pi jump decision
+    ph = ref["phase"][:, 0]
+    d = np.abs(np.abs(np.diff(ph, axis=1)) - np.pi)
+    safe = d.min(axis=1) > 1e-6
+    assert safe.sum() > 0.9 * safe.size
+    assert np.abs(got["phase"][safe, 1] - ref["phase"][safe, 1]).max() < 1e-6
+    assert np.abs(got["phase"][safe, 2] - ref["phase"][safe, 2]).max() < 1e-6
+
+
+def test_config5_n4096_batch_api(br, oracle):
+    """C5: N=4096, K=4, band 9-200, stride 15 through gpu_submit_extract_cycles_batch."""
+    s = synth.random_walk(4, 4096 + 300)
+    st, jid = br.gpu_submit_extract_cycles_batch(s, 4096, 1, 4, 9.0, 200.0, 60.0, 1, 10, 15)
+    assert st == br.OK and jid != 0, br.last_error()
+    nwin = 301
+    out = np.zeros(nwin * 4 * 15)
+    for _ in range(20000):
+        st, n, ready = br.gpu_try_get_cycles_batch(jid, out)
+        if st == br.OK and ready:
+            break
+        assert st == br.NOT_READY
+    assert ready == 1 and n == nwin * 4
+    assert br.gpu_free_job(jid) == br.OK
+    cfg = oracle.default_cfg(4096, top_k=4, min_period=9.0, max_period=200.0, sample_rate_seconds=60.0)
+    ref = oracle.pipeline_series(s, cfg, oracle.OUT_ROWS | oracle.OUT_BINS)
+    rows = out.reshape(nwin, 4, 15)
+    # period = N / bin is exact: selected bins are bit-exact through the public API
+    assert np.array_equal(np.rint(4096 / rows[..., 2]).astype(int), ref["bins"])
+    assert np.abs(rows[..., 0] - ref["rows"][..., 0]).max() <= REL_TOL * ref["rows"][..., 0].max()
+    assert np.all(rows[..., 14] == 0.0)
+
+
+# ---- prologue variants (A2, A3) -----------------------------------------------------------------
+@pytest.mark.parametrize("wtype", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("detrend", [0, 1, 2])
+def test_prologue_matrix(br, oracle, wtype, detrend):
+    s = synth.random_walk(30 + wtype, 256 + 200)
+    cfg = br.default_cfg(256, top_k=6, min_period=4.0, max_period=100.0, detrend=detrend,
+                         trend_period=64.0, window_type=wtype)
+    got, ref = run_both(br, oracle, s, cfg, br.OUT_SPECTRA | br.OUT_BINS)
+    check_planes(br, got, ref, cfg)
+
+
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096])
+@pytest.mark.parametrize("hop", [1, 5])
+def test_window_lengths_and_hops(br, oracle, n, hop):
+    s = synth.random_walk(40 + n, n + 333)
+    cfg = br.default_cfg(n, hop=hop, top_k=4, min_period=9.0, max_period=200.0)
+    got, ref = run_both(br, oracle, s, cfg, br.OUT_SPECTRA | br.OUT_BINS | br.OUT_WAVES)
+    check_planes(br, got, ref, cfg)
+
+
+# ---- edge cases ---------------------------------------------------------------------------------
+def test_flat_market_ties_resolve_by_bin_order(br, oracle):
+    s = np.full(1500, 1.2345)
+    cfg = br.default_cfg(1024, top_k=8)
+    got, ref = run_both(br, oracle, s, cfg, br.OUT_BINS | br.OUT_SPECTRA)
+    assert np.array_equal(got["bins"], ref["bins"])
+    assert np.all(got["bins"] == np.arange(6, 14))
+
+
+def test_quantised_prices_with_long_flat_runs(br, oracle):
+    rng = np.random.default_rng(9)
+    s = np.round(1.1 + 1e-5 * np.cumsum(rng.integers(-1, 2, 3000) * (rng.random(3000) < 0.05)), 5)
+    cfg = br.default_cfg(512, top_k=8, min_period=9.0, max_period=200.0)
+    got, ref = run_both(br, oracle, s, cfg, br.OUT_BINS | br.OUT_SPECTRA)
+    check_planes(br, got, ref, cfg)
+
+
+def test_single_window_and_short_series(br, oracle):
+    s = synth.random_walk(50, 1024)
+    cfg = br.default_cfg(1024)
+    got, ref = run_both(br, oracle, s, cfg, br.OUT_BINS | br.OUT_SPECTRA)
+    assert got["bins"].shape == (1, 8)
+    check_planes(br, got, ref, cfg)
+    with pytest.raises(br.WaveSpecError) as e:
+        br.pipeline_host(s[:1000], cfg)
+    assert e.value.status == br.BAD_ARGS
+
+
+def test_top_k_larger_than_band(br, oracle):
+    s = synth.random_walk(51, 700)
+    cfg = br.default_cfg(256, top_k=12, min_period=40.0, max_period=64.0)     # band = bins 4..6
+    got, ref = run_both(br, oracle, s, cfg, br.OUT_BINS | br.OUT_ROWS | br.OUT_WAVES)
+    assert np.array_equal(got["bins"], ref["bins"])
+    assert np.all(got["bins"][:, 3:] == -1) and np.all(got["rows"][:, 3:, :] == 0.0)
+    check_planes(br, got, ref, cfg)
+
+
+@pytest.mark.parametrize("stride", [1, 4, 8, 12, 15, 20])
+def test_row_strides(br, oracle, stride):
+    s = synth.random_walk(52, 900)
+    cfg = br.default_cfg(512, top_k=4, row_stride=stride, min_period=9.0, max_period=200.0)
+    got, ref = run_both(br, oracle, s, cfg, br.OUT_ROWS)
+    assert got["rows"].shape[-1] == stride
+    m = min(stride, 15)
+    assert np.abs(got["rows"][..., 0] - ref["rows"][..., 0]).max() <= REL_TOL * ref["rows"][..., 0].max()
+    if stride > 15:
+        assert np.all(got["rows"][..., 15:] == 0.0)
+    if m >= 3:
+        assert np.array_equal(got["rows"][..., 2], ref["rows"][..., 2])
+
+
+def test_selection_sort_rule_ties_and_k_ge_1(br, oracle):
+    s = np.full(900, 1.5)                                   # all in-band powers equal (zero)
+    cfg = br.default_cfg(256, top_k=6, min_period=2.0, max_period=1e9, select=br.SELECT_SORT)
+    got, ref = run_both(br, oracle, s, cfg, br.OUT_BINS)
+    assert np.array_equal(got["bins"], ref["bins"])
+    assert got["bins"].min() >= 1
+
+
+# ---- A9 / A10 sequential recursions -------------------------------------------------------------
+def test_kalman4d_bit_exact_long(br, oracle):
+    s = synth.random_walk_batch(60, 5, 64 + 20000)
+    cfg = br.default_cfg(64, outputs=br.OUT_KALMAN)
+    got = br.pipeline_host(s, cfg, br.OUT_KALMAN)
+    for i in range(5):
+        ref = oracle.kalman4d_series(s[i][63:])
+        assert np.array_equal(got["kalman"][i], ref)
+
+
+def test_kalman4d_parameter_variants(br, oracle):
+    s = synth.random_walk(61, 64 + 3000)
+    for over in ({"ema_blend_period": 5.0}, {"adapt_gain": 0.0}, {"clip_std": 0.0},
+                 {"clip_std": 0.5, "meas_noise": 1e-6}, {"follow_strength": 0.01}):
+        cfg = br.default_cfg(64)
+        for k, v in over.items():
+            setattr(cfg.kalman, k, v)
+        got = br.pipeline_host(s, cfg, br.OUT_KALMAN)
+        ocfg = ocfg_from(oracle, cfg)
+        ref = oracle.kalman4d_series(s[63:], ocfg.kalman)
+        assert np.array_equal(got["kalman"], ref), over
+
+
+# ---- A11 PLA ------------------------------------------------------------------------------------
+def test_pla_pivots_bit_exact(br, oracle):
+    n = 512
+    s = synth.random_walk(70, n + 150)
+    lines, bounds, counts = br.pla_windows_host(s, n, 1, 32, 0.0005)
+    for w in range(0, 151, 7):
+        line, st, en, _, _ = oracle.pla_build(s[w:w + n], 32, 0.0005)
+        assert counts[w] == st.size
+        assert np.array_equal(bounds[w, :st.size, 0], st) and np.array_equal(bounds[w, :st.size, 1], en)
+        assert np.array_equal(lines[w], line), "PLA line must be bit-identical (same sums, same order)"
+
+
+def test_pla_feed_pipeline(br, oracle):
+    n = 256
+    s = synth.random_walk(71, n + 120)
+    cfg = br.default_cfg(n, top_k=4, min_period=9.0, max_period=100.0, feed=br.FEED_PLA,
+                         detrend=br.DETREND_IIR, trend_period=64.0, window_type=br.WINDOW_BLACKMAN,
+                         pla_max_segments=16, pla_max_error=0.0003)
+    got, ref = run_both(br, oracle, s, cfg, br.OUT_SPECTRA | br.OUT_BINS | br.OUT_KALMAN)
+    check_planes(br, got, ref, cfg)
+
+
+# ---- imports.mqh job API ------------------------------------------------------------------------
+def test_extract_cycles_sync_and_async(br, oracle):
+    s = synth.random_walk(80, 1024)
+    rows = br.gpu_extract_cycles(s, 4, 9.0, 200.0, 60.0, method=1, out_stride=15)
+    cfg = oracle.default_cfg(1024, top_k=4, min_period=9.0, max_period=200.0)
+    ref = oracle.pipeline_series(s, cfg, oracle.OUT_ROWS | oracle.OUT_BINS)
+    assert rows.shape == (4, 15)
+    assert np.array_equal(np.rint(1024 / rows[:, 2]).astype(int), ref["bins"][0])
+    assert np.all(rows[:, 14] == 0.0)                       # FFT ridge rows are tagged method 0
+
+    jobs = []
+    for i in range(16):                                     # out-of-order polling of many jobs
+        st, jid = br.gpu_submit_extract_cycles(synth.random_walk(81 + i, 1024), 4, 9.0, 200.0, 60.0, 0, 10)
+        assert st == br.OK and jid != 0
+        jobs.append(jid)
+    buf = np.zeros((4, 15))
+    for i in reversed(range(16)):
+        for _ in range(100000):
+            st, n, ready = br.gpu_try_get_cycles(jobs[i], buf, 15, 4)
+            if st != br.NOT_READY:
+                break
+        assert st == br.OK and ready == 1 and n == 4
+        r = oracle.pipeline_series(synth.random_walk(81 + i, 1024), cfg, oracle.OUT_BINS)
+        assert np.array_equal(np.rint(1024 / buf[:, 2]).astype(int), r["bins"][0])
+        assert br.gpu_free_job(jobs[i]) == br.OK
+    assert br.gpu_free_job(jobs[0]) == br.BAD_ARGS          # already freed
+    st, n, ready = br.gpu_try_get_cycles(123456789, buf, 15, 4)
+    assert st == br.BAD_ARGS and ready == 0
+
+
+def test_free_in_flight_job_and_reinit(br):
+    s = synth.random_walk(90, 200000)
+    st, jid = br.gpu_submit_extract_cycles_batch(s, 1024, 1, 8, 18.0, 200.0, 60.0, 0, 10, 15)
+    assert st == br.OK
+    assert br.gpu_free_job(jid) == br.OK                    # tolerated while still running
+    assert br.gpu_init(0, 64) == br.OK                      # idempotent
+    st, jid = br.gpu_submit_extract_cycles_batch(s[:100], 1024, 1, 8, 18.0, 200.0, 60.0, 0, 10, 15)
+    assert st == br.BAD_ARGS and jid == 0
+    st, jid = br.gpu_submit_extract_cycles_batch(s, 8196, 1, 8, 18.0, 200.0, 60.0, 0, 10, 15)
+    assert st == br.BAD_ARGS                                # non power of two (1.0.4-old default)
+
+
+def test_last_error_utf16_contract(br):
+    buf = (C.c_uint16 * 8)()
+    with pytest.raises(br.WaveSpecError):
+        br.gpu_fft_real_forward(np.zeros(3))
+    n = br.lib().gpu_get_last_error_w(buf, 8)
+    assert n == 8 and buf[7] == 0                           # truncated, terminator counted
+    assert br.lib().gpu_get_last_error_w(buf, 0) == 0
