@@ -172,8 +172,8 @@ int get_apow(int N, double alpha, const double** out) {
 
 int validate_cfg(const wavespec_pipeline_cfg* c, int32_t series_len) {
     if (!c) return fail(WAVESPEC_BAD_ARGS, "cfg is null");
-    if (!is_pow2(c->window_len) || c->window_len < 2 || c->window_len > 16384)
-        return fail(WAVESPEC_BAD_ARGS, "window_len must be a power of two in [2, 16384]");
+    if (!is_pow2(c->window_len) || c->window_len < 2 || c->window_len > 8192)
+        return fail(WAVESPEC_BAD_ARGS, "window_len must be a power of two in [2, 8192]");
     if (c->hop < 1) return fail(WAVESPEC_BAD_ARGS, "hop must be >= 1");
     if (c->top_k < 1 || c->top_k > ws::kMaxTopK) return fail(WAVESPEC_BAD_ARGS, "top_k must be in [1, 32]");
     if (c->row_stride < 1) return fail(WAVESPEC_BAD_ARGS, "row_stride must be >= 1");
@@ -571,7 +571,7 @@ int32_t gpu_fft_real_inverse(const double* in_spec, int32_t len, double* out) {
     int rc = ensure_open();
     if (rc) return rc;
     if (!in_spec || !out) return fail(WAVESPEC_BAD_ARGS, "null buffer");
-    if (!is_pow2(len) || len < 4 || len > 16384) return fail(WAVESPEC_BAD_ARGS, "len must be a power of two in [4, 16384]");
+    if (!is_pow2(len) || len < 4 || len > 8192) return fail(WAVESPEC_BAD_ARGS, "len must be a power of two in [4, 8192]");
     const double2* tw;
     if ((rc = get_twiddles(len, &tw))) return rc;
     DeviceBuf din, dout;

@@ -63,11 +63,11 @@ cudaError_t launch_inverse_real(const double* d_spec, int32_t N, int32_t n_windo
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(inverse_real_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 232448) return cudaErrorInvalidValue;
     inverse_real_kernel<<<n_windows, 128, smem, stream>>>(d_spec, N, log2N, tw, d_out);
     return cudaGetLastError();
 }

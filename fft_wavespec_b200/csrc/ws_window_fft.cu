@@ -104,7 +104,7 @@ window_fft_kernel(const Params p) {
     double2* bufA = reinterpret_cast<double2*>(delta + ((T + 1) & ~1));
     double2* bufB = bufA + (size_t)wpc * M;
     int* ord = reinterpret_cast<int*>(bufB + (size_t)wpc * M);
-    double* scr = reinterpret_cast<double*>(ord + (((size_t)wpc * M + 1) & ~(size_t)1));  // IIR scratch
+    double* scr = reinterpret_cast<double*>(ord + (p.select == 1 ? (((size_t)wpc * M + 1) & ~(size_t)1) : 0));  // IIR scratch
 
     const int pro_mode = (from_feed && p.detrend == 1) ? 0 : p.detrend;
     const double* src = p.series + (int64_t)s * p.series_stride + w0 * p.hop;
@@ -324,7 +324,8 @@ size_t window_fft_smem_bytes(const Params& p, int tile_windows) {
     if (wpc > 4) wpc = 4;
     size_t Lt = p.feed ? (size_t)wpc * N : (size_t)(tile_windows - 1) * p.hop + N;
     size_t doubles = ((Lt + 1) & ~(size_t)1) + ((tile_windows + 1) & ~1);
-    size_t bytes = doubles * 8 + 2 * (size_t)wpc * M * 16 + (((size_t)wpc * M + 1) & ~(size_t)1) * 4;
+    size_t bytes = doubles * 8 + 2 * (size_t)wpc * M * 16;
+    if (p.select == 1) bytes += (((size_t)wpc * M + 1) & ~(size_t)1) * 4;
     if (p.detrend == 1) bytes += (Lt + kThreads) * 8;
     return bytes;
 }
@@ -339,6 +340,7 @@ int window_fft_pick_tile(const Params& p) {
     if (wpc > 4) wpc = 4;
     if (p.feed) return wpc;
     long budget = 4096 > N + 63 ? 4096 : N + 63;  // doubles
+    if (N >= 8192) budget = N;                    // shared memory is full: one window per tile
     long t = (budget - N) / p.hop + 1;
     if (t < 1) t = 1;
     if (t > 64) t = 64;
@@ -354,11 +356,11 @@ cudaError_t launch_window_fft(Params p, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(window_fft_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 232448) return cudaErrorInvalidValue;
     dim3 grid((unsigned)((p.chunk_nwin + p.tile_windows - 1) / p.tile_windows), (unsigned)p.n_series);
     window_fft_kernel<<<grid, kThreads, smem, stream>>>(p);
     return cudaGetLastError();

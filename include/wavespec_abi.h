@@ -70,7 +70,7 @@ WAVESPEC_API int32_t gpu_init(int32_t device_index, int32_t stream_count);
 WAVESPEC_API void gpu_shutdown(void);
 
 /* imports.mqh:8.  Real -> half-complex forward FFT, synchronous.  `len` is a power of two
- * in [2, 65536]; out[2k] = Re X[k], out[2k+1] = Im X[k], k = 0..len/2-1 (Nyquist dropped),
+ * in [2, 8192]; out[2k] = Re X[k], out[2k+1] = Im X[k], k = 0..len/2-1 (Nyquist dropped),
  * unnormalised, X[k] = sum x[n] e^{-2 pi i k n / len}.  Contract pinned by
  * Legacy/WaveSpecZZ_1.0.4-new.mq5:3171-3194 vs :3208 (CPU FourierTransformManual). */
 WAVESPEC_API int32_t gpu_fft_real_forward(const double* in, int32_t len, double* out);
@@ -167,7 +167,7 @@ typedef struct wavespec_kalman4d_params {
 } wavespec_kalman4d_params;
 
 typedef struct wavespec_pipeline_cfg {
-    int32_t window_len;        /* power of two, 64..4096                                   */
+    int32_t window_len;        /* power of two, 2..8192                                   */
     int32_t hop;               /* >= 1                                                     */
     int32_t top_k;             /* 1..32                                                    */
     int32_t row_stride;        /* >= 1; min(row_stride,15) fields written per row          */
