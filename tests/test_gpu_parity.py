@@ -224,6 +224,54 @@ def test_config5_n4096_batch_api(br, oracle):
     assert np.all(rows[..., 14] == 0.0)
 
 
+# ---- shared-butterfly sliding kernel (plain hop-1 path) ------------------------------------------
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096])
+def test_sliding_shared_kernel_all_lengths_and_ragged_tiles(br, oracle, n):
+    # series lengths chosen so the last tile is partial and the first tile is the only full one
+    tiles = {256: 128, 512: 64, 1024: 32, 2048: 16, 4096: 8}[n]
+    for extra in (0, 1, tiles - 1, tiles, 2 * tiles + 3):
+        s = synth.random_walk_batch(200 + n, 2, n + extra)
+        cfg = br.default_cfg(n, top_k=8, min_period=9.0, max_period=200.0)
+        out = br.OUT_SPECTRA | br.OUT_BINS | br.OUT_ROWS | br.OUT_WAVES
+        got = br.pipeline_host(s, cfg, out)
+        assert br.last_kernel() == "sliding_shared"
+        for i in range(2):
+            ref = oracle.pipeline_series(s[i], ocfg_from(oracle, cfg), out)
+            check_planes(br, {k: v[i] for k, v in got.items()}, ref, cfg)
+            # off-DC bins: error relative to the largest non-DC bin of the window
+            assert rel_err(got["spectra"][i][:, 2:], ref["spectra"][:, 2:]) < 1e-12
+
+
+def test_sliding_shared_rows_only_and_sort_rule(br, oracle):
+    s = synth.random_walk(210, 1024 + 777)
+    for sel in (br.SELECT_INSERTION, br.SELECT_SORT):
+        cfg = br.default_cfg(1024, top_k=8, min_period=12.0, max_period=256.0, select=sel)
+        out = br.OUT_BINS | br.OUT_ROWS | br.OUT_WKALMAN
+        got, ref = run_both(br, oracle, s, cfg, out)
+        assert br.last_kernel() == "sliding_shared"
+        check_planes(br, got, ref, cfg)
+
+
+def test_sliding_shared_long_series_spot_checks(br, oracle):
+    """200k bars through the batch API; windows spot-checked against the oracle, every selected
+    bin compared on a strided subset."""
+    n = 1024
+    s = synth.random_walk(220, 200000)
+    cfg = br.default_cfg(n, top_k=8, outputs=br.OUT_BINS | br.OUT_SPECTRA)
+    got = br.pipeline_host(s, cfg)
+    assert br.last_kernel() == "sliding_shared"
+    nw = got["bins"].shape[0]
+    ocfg = ocfg_from(oracle, cfg)
+    for w0 in (0, 31, 32, 12345, nw - 40):
+        seg = s[w0:w0 + n + 39]
+        ref = oracle.pipeline_series(seg, ocfg, oracle.OUT_BINS | oracle.OUT_SPECTRA)
+        assert np.array_equal(got["bins"][w0:w0 + 40], ref["bins"])
+        assert rel_err(got["spectra"][w0:w0 + 40], ref["spectra"]) < REL_TOL
+    # linearity property at full length: spectrum(a*x) == a*spectrum(x) exactly for a power of two
+    got2 = br.pipeline_host(4.0 * s, cfg, br.OUT_SPECTRA)
+    assert np.array_equal(got2["spectra"], 4.0 * got["spectra"])
+
+
 # ---- prologue variants (A2, A3) -----------------------------------------------------------------
 @pytest.mark.parametrize("wtype", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("detrend", [0, 1, 2])
