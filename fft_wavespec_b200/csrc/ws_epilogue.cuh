@@ -129,4 +129,129 @@ __device__ __forceinline__ void warp_select_emit(const Params& p, double* pw, co
     }
 }
 
+
+// ---- batched form of the insertion rule (A7a): several windows per warp ------------------------
+// The warp is split into groups of Lg lanes (Lg a power of two >= K); each group owns one window,
+// so the selection shuffles of 32/Lg windows issue together and the row arithmetic (sqrt, atan2)
+// runs on all 32 lanes instead of K.  Rows are staged in shared memory and leave as contiguous
+// 128-bit stores (rows of consecutive windows are contiguous in the output plane).
+//
+// pw    : shared, [wpb][band] powers of the wpb windows of this batch (destroyed)
+// xb    : shared, [wpb][band] complex bins (band-relative index)
+// lo    : first bin of the band;  nvalid : windows of the batch that exist (<= wpb)
+// gw0   : global window index of the batch's first window (series * nwin + window)
+// stage : shared, per-warp scratch of 32 * 16 doubles (used when row_stride <= 16)
+__device__ __forceinline__ void warp_select_emit_batch(const Params& p, double* pw, const double2* xb,
+                                                       int band, int lo, int Lg, int nvalid, int64_t gw0,
+                                                       double* stage) {
+    const int lane = threadIdx.x & 31;
+    const int g = lane / Lg, l = lane - g * Lg;
+    const int N = p.N, K = p.K;
+    double* pwb = pw + g * band;
+    const double2* xbb = xb + g * band;
+    const bool live = g < nvalid;
+
+    double bsum = 0.0;
+    if (live) for (int e = l; e < band; e += Lg) bsum += pwb[e];
+    for (int m = Lg >> 1; m >= 1; m >>= 1) bsum += shfl_xor_d(bsum, m);
+
+    int my_pos = -1;
+    double my_pow = -1.0;
+    for (int r = 0; r < K; r++) {
+        double bp = -1.0; int bpos = 0x7fffffff;
+        if (live)
+            for (int e = l; e < band; e += Lg) {
+                // ascending scan inside a lane: an equal power met later never displaces the earlier
+                // (lower) bin, so strict '>' alone implements the tie rule here
+                double v = pwb[e];
+                if (v > bp) { bp = v; bpos = e; }
+            }
+        for (int m = Lg >> 1; m >= 1; m >>= 1) {
+            double op = shfl_xor_d(bp, m);
+            int opos = __shfl_xor_sync(0xffffffffu, bpos, m);
+            if (better(op, opos, bp, bpos)) { bp = op; bpos = opos; }
+        }
+        if (bpos != 0x7fffffff) {
+            if ((bpos & (Lg - 1)) == l) pwb[bpos] = -2.0;      // the owning lane retires it (-2 < -1)
+            if (l == r) { my_pos = bpos; my_pow = bp; }
+        }
+    }
+
+    const bool has_row = live && l < K;
+    const int my_bin = my_pos >= 0 ? lo + my_pos : -1;
+    double re = 0.0, im = 0.0;
+    if (has_row && my_pos >= 0) { double2 x = xbb[my_pos]; re = x.x; im = x.y; }
+    const int64_t slot = (gw0 + g) * K + l;
+    if (has_row) {
+        if (p.bins) p.bins[slot] = my_bin;
+        const double nn = (double)(N - 1);
+        if (p.waves) {
+            double wv = 0.0;
+            if (my_bin > 0) {
+                double mag = sqrt(my_pow);
+                double ph = atan2(im, re);
+                wv = (mag / (double)N) * cos(ph + 2.0 * kPi * (double)my_bin * nn / (double)N);
+            }
+            p.waves[slot] = wv;
+        }
+        if (p.contrib) {
+            double cv = 0.0;
+            if (my_bin >= 0) {
+                double sn, cs;
+                sincos(2.0 * kPi * my_bin * nn / N, &sn, &cs);
+                cv = (2.0 / N) * (re * cs - im * sn);
+            }
+            p.contrib[slot] = cv;
+        }
+    }
+    if (p.rows) {
+        double f[kRowFields];
+#pragma unroll
+        for (int i = 0; i < kRowFields; i++) f[i] = 0.0;
+        if (has_row && my_bin > 0) {
+            f[0] = 2.0 * sqrt(my_pow) / (double)N;
+            f[1] = (double)my_bin / (double)N;
+            f[2] = (double)N / (double)my_bin;
+            // phase at the newest sample: atan2 + 2 pi k (N-1)/N + pi/2, wrapped to [-pi, pi].
+            // 2 pi k (N-1)/N == -2 pi k/N (mod 2 pi); the small angle keeps the wrap to one step.
+            double ph = atan2(im, re) + (0.5 * kPi - 2.0 * kPi * (double)my_bin / (double)N);
+            if (ph > kPi) ph -= 2.0 * kPi;
+            if (ph < -kPi) ph += 2.0 * kPi;
+            f[3] = ph;
+            double d = 0.5 * kPi - ph;                  // bars to the next extremum of amp*sin
+            if (d < 0.0) d += kPi;
+            if (d >= kPi) d -= kPi;
+            f[4] = d / (2.0 * kPi * f[1]);
+            f[5] = f[4] * p.sample_rate_seconds;
+            f[6] = bsum > 0.0 ? my_pow / bsum : 0.0;
+        }
+        const int rs = p.row_stride;
+        if (rs <= 16) {
+            // stage, then stream out contiguously
+            if (has_row) {
+                double* srow = stage + (g * K + l) * rs;
+#pragma unroll
+                for (int i = 0; i < kRowFields; i++) if (i < rs) srow[i] = f[i];
+                if (rs > kRowFields) srow[kRowFields] = 0.0;
+            }
+            __syncwarp();
+            const int total = nvalid * K * rs;                       // doubles of this batch
+            double* dst = p.rows + gw0 * K * (int64_t)rs;
+            if ((((gw0 * K * (int64_t)rs) | total) & 1) == 0) {
+                const double2* s2 = reinterpret_cast<const double2*>(stage);
+                double2* d2 = reinterpret_cast<double2*>(dst);
+                for (int i = lane; i < (total >> 1); i += 32) __stcs(d2 + i, s2[i]);
+            } else {
+                for (int i = lane; i < total; i += 32) __stcs(dst + i, stage[i]);
+            }
+            __syncwarp();
+        } else if (has_row) {
+            double* row = p.rows + slot * (int64_t)rs;
+#pragma unroll
+            for (int i = 0; i < kRowFields; i++) if (i < rs) row[i] = f[i];
+            for (int i = kRowFields; i < rs; i++) row[i] = 0.0;
+        }
+    }
+}
+
 }  // namespace ws

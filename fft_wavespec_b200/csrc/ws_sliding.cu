@@ -19,6 +19,9 @@
 // Roofline: the only mandatory HBM traffic is 8*hop bytes in + 8*N bytes out per spectrum; the
 // arithmetic is ~N/2 packed butterflies per window (~4.6 kflop-instr at N = 1024), far below the
 // FP64 pipe limit, so the kernel is bound by the spectrum store.
+#include <cstdio>
+#include <cstdlib>
+
 #include "ws_common.cuh"
 #include "ws_epilogue.cuh"
 #include "ws_series.h"
@@ -33,26 +36,56 @@ constexpr int kSlideThreads = 256;
 struct SlideLayout {
     int x_doubles;      // staged samples (even count)
     int arena_off;      // byte offsets inside dynamic shared memory
-    int xb_off, pw_off, ord_off;
+    int xb_off, pw_off, stage_off, ord_off;
     int band;           // captured bins per window
+    int Lg;             // lanes per window in the batched epilogue (power of two >= K)
     int total_bytes;
 };
 
+// Receives the bins of the top pass: streams them to HBM and captures the in-band ones.
+// The eight bins of slot k are +-k + C_J Q: two moving pointers plus compile-time offsets.
+template <int N, bool SPEC, bool SEL>
 struct TopSink {
-    double2* g;             // spectra of this series (nullptr: not requested)
-    double2* xb;            // shared band capture (nullptr: no selection outputs)
-    int N2;                 // N/2 slots per window
+    double2* g;             // spectra of the tile's first window
+    double2* xb;            // shared band capture
     int lo, hi, band;
-    int64_t w0, nwin;
-    __device__ __forceinline__ void put(int pos, int idx, double2 v) {
-        const int64_t w = w0 + pos;
-        if (w >= nwin) return;
-        if (idx == 0) v.y = 0.0;     // slot 0 carries the Nyquist bin in .y: the contract drops it
-        if (g) __stcs(g + w * N2 + idx, v);
-        if (xb && idx >= lo && idx <= hi) xb[pos * band + (idx - lo)] = v;
+    int nvalid;             // windows of this tile that exist
+    // per-thread state
+    int k;
+    unsigned inband;
+    double2 *gpP, *gpM, *xpP, *xpM;
+    bool ok;
+    static constexpr int Q = N / 16, N2 = N / 2;
+    template <int J> __device__ __forceinline__ void mark() {
+        const int idx = ws_slide::SlotOfs<J>::c * Q + ws_slide::SlotOfs<J>::sgn * k;
+        if (idx >= lo && idx <= hi) inband |= 1u << J;
+    }
+    __device__ __forceinline__ void bind(int kk) {
+        k = kk;
+        inband = 0;
+        if (SEL) { mark<0>(); mark<1>(); mark<2>(); mark<3>(); mark<4>(); mark<5>(); mark<6>(); mark<7>(); }
+    }
+    __device__ __forceinline__ void begin(int m) {
+        ok = m < nvalid;
+        if (SPEC) { gpP = g + m * N2 + k; gpM = g + m * N2 - k; }
+        if (SEL) { xpP = xb + (m * band - lo) + k; xpM = xb + (m * band - lo) - k; }
+    }
+    template <int J> __device__ __forceinline__ void put(double2 v) {
+        if (!ok) return;
+        constexpr int c = ws_slide::SlotOfs<J>::c * Q;
+        constexpr bool plus = ws_slide::SlotOfs<J>::sgn > 0;
+        if (SPEC) __stcs((plus ? gpP : gpM) + c, v);
+        if (SEL) if ((inband >> J) & 1u) (plus ? xpP : xpM)[c] = v;
+    }
+    __device__ __forceinline__ void put0(int m, int i, double2 v) {
+        if (m >= nvalid) return;
+        if (i == 0) v.y = 0.0;       // slot 0 carries the Nyquist bin in .y: the contract drops it
+        if (SPEC) __stcs(g + m * N2 + i, v);
+        if (SEL) if (i >= lo && i <= hi) xb[m * band + (i - lo)] = v;
     }
 };
 
+template <int N, bool SPEC, bool SEL>
 __global__ void __launch_bounds__(kSlideThreads, 2)
 sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -63,6 +96,7 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     const int64_t w0 = p.win_offset + (int64_t)blockIdx.x * pl.T;
     const int64_t wend = p.win_offset + p.chunk_nwin;
     const double* src = p.series + (int64_t)s * p.series_stride;
+    const int nvalid = (int)((wend - w0) < pl.T ? (wend - w0) : pl.T);
 
     // 1. stage the tile (+ halo); beyond the series the samples only feed windows that are never stored
     for (int i = tid; i < pl.x_len; i += kSlideThreads) {
@@ -73,45 +107,52 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     // 2. deepest level straight from the samples
     ws_slide::bottom_level(tid, kSlideThreads, x, pl, p.tw, arena);
     __syncthreads();
-    // 3. fused passes down to level 3
+    // 3. chain-free radix-8 passes down to level 3
     for (int i = pl.nst; i >= 2; i--) {
         ws_slide::SmemSink sink{arena + pl.off[i - 1], pl.stride[i - 1]};
-        ws_slide::fused_pass(tid, kSlideThreads, arena + pl.off[i], pl.stride[i], pl.Q[i], 1 << (3 * (i - 1)),
-                             pl.P[i - 1], 1, p.tw, pl.N, 3 * (i - 1), sink);
+        ws_slide::direct_pass(tid, kSlideThreads, arena + pl.off[i], pl.stride[i], pl.Q[i], 1 << (3 * (i - 1)),
+                              pl.P[i - 1], p.tw, pl.N, 3 * (i - 1), sink);
         __syncthreads();
     }
     // 4. top pass: level 3 -> full spectra, streamed to HBM
-    const bool want_sel = (p.bins || p.rows || p.waves || p.contrib) && lay.band > 0;
-    TopSink top;
-    top.g = p.spectra ? reinterpret_cast<double2*>(p.spectra) + (int64_t)s * p.nwin * (pl.N / 2) : nullptr;
-    top.xb = want_sel ? reinterpret_cast<double2*>(smem_raw + lay.xb_off) : nullptr;
-    top.N2 = pl.N / 2;
+    const bool want_sel = SEL;
+    TopSink<N, SPEC, SEL> top;
+    top.g = SPEC ? reinterpret_cast<double2*>(p.spectra) + ((int64_t)s * p.nwin + w0) * (N / 2) : nullptr;
+    top.xb = (SEL && lay.band > 0) ? reinterpret_cast<double2*>(smem_raw + lay.xb_off) : nullptr;
     top.lo = p.band_lo; top.hi = p.band_hi; top.band = lay.band;
     if (p.select == 1 && top.lo < 1) top.lo = 1;
-    top.w0 = w0; top.nwin = wend;
-    ws_slide::fused_pass(tid, kSlideThreads, arena + pl.off[1], pl.stride[1], pl.Q[1], 1, pl.T, pl.S, p.tw,
-                         pl.N, 0, top);
-    if (!(p.bins || p.rows || p.waves || p.contrib)) return;
+    if (lay.band <= 0) { top.lo = 1; top.hi = 0; }      // empty band: capture nothing
+    top.nvalid = nvalid;
+    ws_slide::chain_pass<N>(tid, kSlideThreads, arena + pl.off[1], pl.T, pl.S, p.tw, top);
+    if (!want_sel) return;
     __syncthreads();
-    // 5. warp-per-window selection + rows
+    // 5. selection + rows
     const int lane = tid & 31, warp = tid >> 5;
-    int nvalid = (int)((wend - w0) < pl.T ? (wend - w0) : pl.T);
-    if (lay.band > 0) {
-        double* pw = reinterpret_cast<double*>(smem_raw + lay.pw_off) + warp * lay.band;
-        int* ord = reinterpret_cast<int*>(smem_raw + lay.ord_off) + warp * lay.band;
-        const int lo = top.lo;
+    const int64_t gw_tile = (int64_t)s * p.nwin + w0;
+    if (lay.band <= 0) {
+        for (int wl = warp; wl < nvalid; wl += kSlideThreads / 32)    // empty band: every slot absent
+            warp_select_emit(p, nullptr, nullptr, nullptr, gw_tile + wl);
+        return;
+    }
+    const int band = lay.band, lo = top.lo;
+    double* pw = reinterpret_cast<double*>(smem_raw + lay.pw_off);
+    for (int i = tid; i < nvalid * band; i += kSlideThreads) { double2 v = top.xb[i]; pw[i] = v.x * v.x + v.y * v.y; }
+    __syncthreads();
+    if (p.select == 1) {
+        int* ord = reinterpret_cast<int*>(smem_raw + lay.ord_off) + warp * band;
         for (int wl = warp; wl < nvalid; wl += kSlideThreads / 32) {
-            const double2* xb = top.xb + wl * lay.band;
-            for (int b = lane; b < lay.band; b += 32) { double2 v = xb[b]; pw[b] = v.x * v.x + v.y * v.y; }
-            __syncwarp();
-            warp_select_emit(p, pw - lo, xb - lo, ord, (int64_t)s * p.nwin + w0 + wl);
+            warp_select_emit(p, pw + wl * band - lo, top.xb + wl * band - lo, ord, gw_tile + wl);
             __syncwarp();
         }
     } else {
-        // empty band: every slot is absent
-        for (int wl = warp; wl < nvalid; wl += kSlideThreads / 32)
-            warp_select_emit(p, nullptr, nullptr, nullptr, (int64_t)s * p.nwin + w0 + wl);
+        const int wpb = 32 / lay.Lg;                                  // windows per warp batch
+        double* stage = reinterpret_cast<double*>(smem_raw + lay.stage_off) + warp * 512;
+        for (int b0 = warp * wpb; b0 < nvalid; b0 += (kSlideThreads / 32) * wpb) {
+            const int nb = (nvalid - b0) < wpb ? (nvalid - b0) : wpb;
+            warp_select_emit_batch(p, pw + b0 * band, top.xb + b0 * band, band, lo, lay.Lg, nb, gw_tile + b0, stage);
+        }
     }
+    (void)lane;
 }
 
 static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
@@ -124,6 +165,10 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
         case 4096: T = 8;   S = 1;  break;
         default: return false;
     }
+    if (const char* ov = getenv("WAVESPEC_TILE")) {       // tuning hook: "T,S"
+        int t = 0, sc = 0;
+        if (sscanf(ov, "%d,%d", &t, &sc) == 2 && t > 0 && sc > 0) { T = t; S = sc; }
+    }
     if (!ws_slide::plan_make(pl, p.N, T, S)) return false;
     int lo = p.band_lo, hi = p.band_hi;
     if (p.select == 1 && lo < 1) lo = 1;
@@ -134,13 +179,27 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
     const int below3 = lay.arena_off + pl.off[1] * 16;               // bytes below the level-3 array
     const int work_end = lay.arena_off + pl.arena_slots * 16;
     const int xb_bytes = pl.T * lay.band * 16;
-    // the band capture is written while level 3 is still being read: it may only reuse what
-    // lies below level 3; pw / ord are used after the barrier and may overlay anything
-    lay.xb_off = (xb_bytes <= below3) ? 0 : work_end;
-    lay.pw_off = lay.xb_off + xb_bytes;
+    // lanes per window in the batched epilogue: >= K and enough lanes that a lane scans <= 8 bins
+    int need = p.K > (lay.band + 7) / 8 ? p.K : (lay.band + 7) / 8;
+    lay.Lg = 1;
+    while (lay.Lg < need && lay.Lg < 32) lay.Lg <<= 1;
+    // The band capture is written while level 3 is still being read: it may only reuse what lies
+    // below level 3, otherwise it gets its own space after the work area.  pw / stage / ord are
+    // used after the barrier that follows the top pass: they overlay the (dead) work area.
     const int warps = kSlideThreads / 32;
-    lay.ord_off = lay.pw_off + warps * lay.band * 8;
-    int end = lay.ord_off + warps * lay.band * 4;
+    lay.xb_off = (xb_bytes <= below3) ? 0 : work_end;
+    const int xb_end = lay.xb_off + xb_bytes;
+    lay.pw_off = (lay.xb_off == 0) ? xb_bytes : 0;
+    lay.stage_off = lay.pw_off + pl.T * lay.band * 8;
+    lay.ord_off = lay.stage_off + warps * 512 * 8;
+    int end = lay.ord_off + (p.select == 1 ? warps * lay.band * 4 : 0);
+    if (lay.xb_off != 0 && end > work_end) {
+        // overlay does not fit under the capture: move the capture up
+        lay.xb_off = (end + 15) & ~15;
+    }
+    if (xb_end > end) end = xb_end;
+    if (lay.xb_off + xb_bytes > end) end = lay.xb_off + xb_bytes;
+    if (!sel) end = 0;
     lay.total_bytes = end > work_end ? end : work_end;
     lay.total_bytes = (lay.total_bytes + 15) & ~15;
     return lay.total_bytes <= 232448;
@@ -152,20 +211,42 @@ bool sliding_shared_supported(const Params& p) {
     return pick_plan(p, pl, lay);
 }
 
-cudaError_t launch_sliding_shared(Params p, cudaStream_t stream) {
-    Plan pl; SlideLayout lay;
-    if (!pick_plan(p, pl, lay)) return cudaErrorInvalidValue;
+template <int N, bool SPEC, bool SEL>
+static cudaError_t launch_one(const Params& p, const Plan& pl, const SlideLayout& lay, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(sliding_shared_kernel,
+        cudaError_t e = cudaFuncSetAttribute(sliding_shared_kernel<N, SPEC, SEL>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    p.tile_windows = pl.T;
     dim3 grid((unsigned)((p.chunk_nwin + pl.T - 1) / pl.T), (unsigned)p.n_series);
-    sliding_shared_kernel<<<grid, kSlideThreads, lay.total_bytes, stream>>>(p, pl, lay);
+    sliding_shared_kernel<N, SPEC, SEL><<<grid, kSlideThreads, lay.total_bytes, stream>>>(p, pl, lay);
     return cudaGetLastError();
+}
+
+template <int N>
+static cudaError_t launch_n(const Params& p, const Plan& pl, const SlideLayout& lay, cudaStream_t stream) {
+    const bool spec = p.spectra != nullptr;
+    const bool sel = p.bins || p.rows || p.waves || p.contrib;
+    if (spec && sel) return launch_one<N, true, true>(p, pl, lay, stream);
+    if (spec) return launch_one<N, true, false>(p, pl, lay, stream);
+    if (sel) return launch_one<N, false, true>(p, pl, lay, stream);
+    return cudaSuccess;
+}
+
+cudaError_t launch_sliding_shared(Params p, cudaStream_t stream) {
+    Plan pl; SlideLayout lay;
+    if (!pick_plan(p, pl, lay)) return cudaErrorInvalidValue;
+    p.tile_windows = pl.T;
+    switch (p.N) {
+        case 256: return launch_n<256>(p, pl, lay, stream);
+        case 512: return launch_n<512>(p, pl, lay, stream);
+        case 1024: return launch_n<1024>(p, pl, lay, stream);
+        case 2048: return launch_n<2048>(p, pl, lay, stream);
+        case 4096: return launch_n<4096>(p, pl, lay, stream);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 }  // namespace ws

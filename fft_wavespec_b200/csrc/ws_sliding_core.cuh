@@ -18,10 +18,11 @@
 //        F(s,m)[k] = A[k] + t          F(s,m)[2Q - k] = conj(A[k] - t)          0 < k < Q
 //        slot 0 = (A0 + B0, A0 - B0)   F(s,m)[Q] = (A[Q], -B[Q])                (A[Q], B[Q] real)
 //
-// Three levels are fused per pass (radix-8 in registers): a thread owns slot k of level s+3 and
-// one residue r of the positions modulo D = 2^s, walks the chain m = r, r+D, r+2D, ... and keeps
-// the intermediate levels in registers, reading ONE new slot and producing the EIGHT slots of
-// F(s, m) per step: 7 packed butterflies per step for a general slot, 4 for the packed slot 0.
+// Three levels are fused per pass (radix-8 in registers).  The top pass (levels 3 -> 0), which is
+// ~85% of the arithmetic and produces the output, runs as register CHAINS: a thread owns slot k of
+// level 3, walks consecutive windows m, m+1, ... keeping the intermediate levels in registers,
+// reads ONE new slot and emits EIGHT bins per window with 7 packed butterflies.  The lower
+// passes are chain-free (12 butterflies per item) so that the whole CTA can work on them.
 #pragma once
 
 #ifdef __CUDACC__
@@ -60,7 +61,7 @@ WS_HD bool plan_make(Plan& pl, int N, int T, int S) {
     pl.log2N = l;
     if ((1 << l) != N || N < 256 || N > 4096) return false;
     pl.T = T; pl.S = S;
-    if (S < 1 || T % S) return false;
+    if (S < 1 || T % S || (T / S) % 4) return false;
     pl.nst = (N <= 1024) ? 2 : 3;
     pl.sb = 3 * pl.nst;
     pl.Lb = N >> pl.sb;
@@ -118,116 +119,211 @@ struct SmallRdft<2> {
     }
 };
 
-// ---- one fused pass (levels s+3 -> s) ---------------------------------------------------------
-// Sink: receives slot `idx` of F(s, position pos).
-//
-// in       : level s+3 vectors, `in_stride` slots apart, Q slots each
-// D        : 2^s (chain stride in positions)
-// n_out    : number of level-s positions to produce (positions 0 .. n_out-1, tile relative)
-// S        : sub-chains per residue (top pass only; 1 otherwise).  Sub-chain c covers the
-//            ceil-split range of chain steps.
+// ---- radix-8 packed butterflies (levels s+3 -> s) -------------------------------------------
+// Output slot order of a general slot k (Q = slots of the input level):
+//   o[0]=k  o[1]=8Q-k  o[2]=4Q-k  o[3]=4Q+k  o[4]=2Q-k  o[5]=6Q+k  o[6]=2Q+k  o[7]=6Q-k
+struct Tw7 { double2 w2, w1a, w1b, w0a, w0b, w0c, w0d; };
+
+WS_HD Tw7 load_tw7(const double2* tw, int N, int L /* DFT length of the output level = 16Q */, int Q, int k) {
+    const int u2 = N / (L / 4), u1 = N / (L / 2), u0 = N / L;
+    Tw7 t;
+    t.w2 = tw[u2 * k];
+    t.w1a = tw[u1 * k];           t.w1b = tw[u1 * (2 * Q - k)];
+    t.w0a = tw[u0 * k];           t.w0b = tw[u0 * (4 * Q - k)];
+    t.w0c = tw[u0 * (2 * Q - k)]; t.w0d = tw[u0 * (2 * Q + k)];
+    return t;
+}
+
+WS_HD void slot_index8(int Q, int k, int idx[8]) {
+    idx[0] = k;         idx[1] = 8 * Q - k; idx[2] = 4 * Q - k; idx[3] = 4 * Q + k;
+    idx[4] = 2 * Q - k; idx[5] = 6 * Q + k; idx[6] = 2 * Q + k; idx[7] = 6 * Q - k;
+}
+
+// last level of the radix-8 group: F(s,m) = F1(m) (+) F1(m+D)
+WS_HD void level0_general(const double2 f1[4], const double2 g[4], const Tw7& t, double2 o[8]) {
+    bfly(f1[0], g[0], t.w0a, o[0], o[1]);
+    bfly(f1[1], g[1], t.w0b, o[2], o[3]);
+    bfly(f1[2], g[2], t.w0c, o[4], o[5]);
+    bfly(f1[3], g[3], t.w0d, o[6], o[7]);
+}
+
+// chain-free form: the eight inputs I[j] = In(m + j D)[k] -> the eight output slots (12 butterflies)
+WS_HD void radix8_general(const double2 I[8], const Tw7& t, double2 o[8]) {
+    double2 aP, aR, bP, bR, cP, cR, dP, dR;
+    bfly(I[0], I[4], t.w2, aP, aR);     // F2(m)
+    bfly(I[1], I[5], t.w2, bP, bR);     // F2(m+D)
+    bfly(I[2], I[6], t.w2, cP, cR);     // F2(m+2D)
+    bfly(I[3], I[7], t.w2, dP, dR);     // F2(m+3D)
+    double2 f1[4], g[4];
+    bfly(aP, cP, t.w1a, f1[0], f1[1]);  // F1(m)
+    bfly(aR, cR, t.w1b, f1[2], f1[3]);
+    bfly(bP, dP, t.w1a, g[0], g[1]);    // F1(m+D)
+    bfly(bR, dR, t.w1b, g[2], g[3]);
+    level0_general(f1, g, t, o);
+}
+
+// packed slot 0 of the input level: (F[0], F[Q]) both real.  Output slots, in this order:
+//   o[0]=slot 0 packed (F[0], F[8Q])  o[1]=4Q  o[2]=2Q  o[3]=6Q  o[4]=Q  o[5]=7Q  o[6]=3Q  o[7]=5Q
+struct Tw4s { double2 w8, wa, wb, wc; };
+WS_HD Tw4s load_tw4s(const double2* tw, int N, int L, int Q) {
+    const int u1 = N / (L / 2), u0 = N / L;
+    Tw4s t;
+    t.w8 = tw[u1 * Q];          // W_{8Q}^{Q}   = W_8
+    t.wa = tw[u0 * 2 * Q];      // W_{16Q}^{2Q} = W_8
+    t.wb = tw[u0 * Q];          // W_16
+    t.wc = tw[u0 * 3 * Q];      // W_16^3
+    return t;
+}
+WS_HD void slot_index8_special(int Q, int idx[8]) {
+    idx[0] = 0; idx[1] = 4 * Q; idx[2] = 2 * Q; idx[3] = 6 * Q; idx[4] = Q; idx[5] = 7 * Q; idx[6] = 3 * Q; idx[7] = 5 * Q;
+}
+WS_HD void radix8_special(const double2 I[8], const Tw4s& t, double2 o[8]) {
+    // level s+2 for positions m, m+D, m+2D, m+3D: idx 0, 2Q (real) and Q (complex)
+    double r0[4], r2[4]; double2 cQ[4];
+    for (int j = 0; j < 4; j++) {
+        r0[j] = I[j].x + I[j + 4].x; r2[j] = I[j].x - I[j + 4].x;
+        cQ[j] = make_double2(I[j].y, -I[j + 4].y);
+    }
+    // level s+1 for positions m (from j = 0, 2) and m+D (from j = 1, 3): idx 0, 4Q real; 2Q, Q, 3Q complex
+    double s0[2], s4[2]; double2 c2[2], c1[2], c3[2];
+    for (int j = 0; j < 2; j++) {
+        s0[j] = r0[j] + r0[j + 2]; s4[j] = r0[j] - r0[j + 2];
+        c2[j] = make_double2(r2[j], -r2[j + 2]);
+        bfly(cQ[j], cQ[j + 2], t.w8, c1[j], c3[j]);
+    }
+    o[0] = make_double2(s0[0] + s0[1], s0[0] - s0[1]);
+    o[1] = make_double2(s4[0], -s4[1]);
+    bfly(c2[0], c2[1], t.wa, o[2], o[3]);
+    bfly(c1[0], c1[1], t.wb, o[4], o[5]);
+    bfly(c3[0], c3[1], t.wc, o[6], o[7]);
+}
+
+// ---- chain-free pass (lower levels): one work item per (position, slot) -------------------------
+// Sink: put(pos, idx, value).  12 butterflies per general item instead of the chain's 7, but every
+// item is independent, so the whole CTA works on it (the lower levels are ~12% of the arithmetic).
 template <class Sink>
-WS_HD void fused_pass(int tid, int nthreads, const double2* in, int in_stride, int Q, int D, int n_out,
-                      int S, const double2* tw, int N, int s_level, Sink& sink) {
-    const int L = N >> s_level;                   // DFT length at the output level (= 16 Q)
-    const int chains = S * D * Q;
-    for (int c = tid; c < chains; c += nthreads) {
-        const int k = c % Q;
-        const int r = (c / Q) % D;
-        const int sub = c / (Q * D);
-        // chain steps for residue r: positions r, r+D, ... < n_out
-        const int steps_total = (n_out - r + D - 1) / D;
-        if (steps_total <= 0) continue;
-        const int per = (steps_total + S - 1) / S;
-        const int i0 = sub * per;
-        int i1 = i0 + per;
-        if (i1 > steps_total) i1 = steps_total;
-        if (i0 >= i1) continue;
-        const int m0 = r + i0 * D;
+WS_HD void direct_pass(int tid, int nthreads, const double2* in, int in_stride, int Q, int D, int n_out,
+                       const double2* tw, int N, int s_level, Sink& sink) {
+    const int L = N >> s_level;
+    const int gen = Q - 1;
+    for (int item = tid; item < n_out * gen; item += nthreads) {
+        const int m = item / gen, k = 1 + item - m * gen;
+        const Tw7 t = load_tw7(tw, N, L, Q, k);
+        double2 I[8], o[8];
+        int idx[8];
+        for (int j = 0; j < 8; j++) I[j] = in[(m + j * D) * in_stride + k];
+        radix8_general(I, t, o);
+        slot_index8(Q, k, idx);
+        for (int j = 0; j < 8; j++) sink.put(m, idx[j], o[j]);
+    }
+    const Tw4s ts = load_tw4s(tw, N, L, Q);
+    for (int m = tid; m < n_out; m += nthreads) {
+        double2 I[8], o[8];
+        int idx[8];
+        for (int j = 0; j < 8; j++) I[j] = in[(m + j * D) * in_stride];
+        radix8_special(I, ts, o);
+        slot_index8_special(Q, idx);
+        for (int j = 0; j < 8; j++) sink.put(m, idx[j], o[j]);
+    }
+}
+
+// ---- top pass (levels 3 -> 0, D = 1): register chains over consecutive windows ------------------
+// A thread owns one general slot k of level 3 and one sub-chain of T/S consecutive windows; per
+// window it reads ONE new slot and emits EIGHT bins with 7 packed butterflies.  The packed slot 0
+// has no chain: its eight bins are produced per window by radix8_special (one thread per window).
+//
+// Compile-time N: the eight output bins of slot k are  +-k + C_J  with constant C_J, so a sink can
+// address them as two moving pointers plus immediates.  Only four twiddles are kept in registers;
+// the other three follow from  W^{L/4 - j} = -i conj(W^j)  (bfly_alt).  The loop is unrolled by 4 so
+// the three register queues (inputs: 4 deep, level 2: 2 deep, level 1: 2 deep) rotate by renaming.
+//
+// Sink: bind(k) once per chain; begin(m) once per window; put<J>(value), J = slot_index8 order;
+//       put0(m, idx, value) for the bins that come from the packed slot 0.
+template <int J> struct SlotOfs;    // C_J in units of Q, and the sign of k
+template <> struct SlotOfs<0> { static constexpr int c = 0, sgn = +1; };
+template <> struct SlotOfs<1> { static constexpr int c = 8, sgn = -1; };
+template <> struct SlotOfs<2> { static constexpr int c = 4, sgn = -1; };
+template <> struct SlotOfs<3> { static constexpr int c = 4, sgn = +1; };
+template <> struct SlotOfs<4> { static constexpr int c = 2, sgn = -1; };
+template <> struct SlotOfs<5> { static constexpr int c = 6, sgn = +1; };
+template <> struct SlotOfs<6> { static constexpr int c = 2, sgn = +1; };
+template <> struct SlotOfs<7> { static constexpr int c = 6, sgn = -1; };
+
+// packed butterfly with the twiddle w' = -i conj(w) = (-w.y, -w.x)
+WS_HD void bfly_alt(double2 A, double2 B, double2 w, double2& P, double2& R) {
+    double2 t = make_double2(w.x * B.y - w.y * B.x, -(w.x * B.x + w.y * B.y));
+    P = make_double2(A.x + t.x, A.y + t.y);
+    R = make_double2(A.x - t.x, t.y - A.y);
+}
+
+template <int N> struct TopGeom {
+    static constexpr int Q = N / 16;                                  // slots of a level-3 vector
+    static constexpr int stride = Q >= 64 ? Q : Q + (Q >> 3);         // = Plan::stride[1]
+};
+
+template <int N, class Sink>
+WS_HD void chain_step(const double2*& nxt, double2& qold, double2& f2oP, double2& f2oR, const double2* f1,
+                      double2* g, double2 w2, double2 w1a, double2 w0a, double2 w0c, int m, Sink& sink) {
+    const double2 In = *nxt;
+    nxt += TopGeom<N>::stride;
+    double2 nP, nR;
+    bfly(qold, In, w2, nP, nR);                 // F2(m+3)
+    bfly(f2oP, nP, w1a, g[0], g[1]);            // F1(m+1): idx k, 4Q-k
+    bfly_alt(f2oR, nR, w1a, g[2], g[3]);        //          idx 2Q-k, 2Q+k   (twiddle W^{2Q-k} = -i conj W^k)
+    qold = In; f2oP = nP; f2oR = nR;            // the consumed queue heads are replaced by the newest
+    double2 P, R;
+    sink.begin(m);
+    bfly(f1[0], g[0], w0a, P, R);     sink.template put<0>(P); sink.template put<1>(R);
+    bfly_alt(f1[1], g[1], w0a, P, R); sink.template put<2>(P); sink.template put<3>(R);   // W^{4Q-k}
+    bfly(f1[2], g[2], w0c, P, R);     sink.template put<4>(P); sink.template put<5>(R);   // W^{2Q-k}
+    bfly_alt(f1[3], g[3], w0c, P, R); sink.template put<6>(P); sink.template put<7>(R);   // W^{2Q+k}
+}
+
+template <int N, class Sink>
+WS_HD void chain_pass(int tid, int nthreads, const double2* in, int T, int S, const double2* tw, Sink& sink) {
+    constexpr int Q = TopGeom<N>::Q;
+    constexpr int stride = TopGeom<N>::stride;
+    constexpr int gen = Q - 1;
+    const int per = T / S;                       // multiple of 4 (plan_make)
+    for (int c = tid; c < S * gen; c += nthreads) {
+        const int sub = c / gen, k = 1 + c - sub * gen;
+        const double2 w2 = tw[4 * k];            // W_{N/4}^k (level 2 has DFT length N/4)
+        const double2 w1a = tw[2 * k];           // W_{N/2}^k
+        const double2 w0a = tw[k];               // W_N^k
+        const double2 w0c = tw[2 * Q - k];       // W_N^{2Q-k}
         const double2* src = in + k;
-#define WS_IN(pos) src[(size_t)(pos) * in_stride]
-        if (k != 0) {
-            // twiddles: level s+2 has length L/4, level s+1 L/2, level s L
-            const int u2 = N / (L / 4), u1 = N / (L / 2), u0 = N / L;
-            const double2 w2 = tw[u2 * k];
-            const double2 w1a = tw[u1 * k], w1b = tw[u1 * (2 * Q - k)];
-            const double2 w0a = tw[u0 * k], w0b = tw[u0 * (4 * Q - k)], w0c = tw[u0 * (2 * Q - k)],
-                          w0d = tw[u0 * (2 * Q + k)];
-            double2 q0, q1, q2, q3;               // I_{3..6} relative to the current position
-            double2 f2aP, f2aR, f2bP, f2bR;       // F2(m+D), F2(m+2D)
-            double2 f1[4];                        // F1(m): idx k, 4Q-k, 2Q-k, 2Q+k
-            {
-                double2 I0 = WS_IN(m0), I1 = WS_IN(m0 + D), I2 = WS_IN(m0 + 2 * D);
-                q0 = WS_IN(m0 + 3 * D);
-                q1 = WS_IN(m0 + 4 * D); q2 = WS_IN(m0 + 5 * D); q3 = WS_IN(m0 + 6 * D);
-                double2 f20P, f20R;
-                bfly(I0, q1, w2, f20P, f20R);     // F2(m0)
-                bfly(I1, q2, w2, f2aP, f2aR);     // F2(m0+D)
-                bfly(I2, q3, w2, f2bP, f2bR);     // F2(m0+2D)
-                bfly(f20P, f2bP, w1a, f1[0], f1[1]);
-                bfly(f20R, f2bR, w1b, f1[2], f1[3]);
-            }
-            for (int i = i0; i < i1; i++) {
-                const int m = r + i * D;
-                double2 In = WS_IN(m + 7 * D);
-                double2 nP, nR;
-                bfly(q0, In, w2, nP, nR);         // F2(m+3D)
-                double2 g[4];
-                bfly(f2aP, nP, w1a, g[0], g[1]);  // F1(m+D)
-                bfly(f2aR, nR, w1b, g[2], g[3]);
-                double2 P, R;
-                bfly(f1[0], g[0], w0a, P, R); sink.put(m, k, P);         sink.put(m, 8 * Q - k, R);
-                bfly(f1[1], g[1], w0b, P, R); sink.put(m, 4 * Q - k, P); sink.put(m, 4 * Q + k, R);
-                bfly(f1[2], g[2], w0c, P, R); sink.put(m, 2 * Q - k, P); sink.put(m, 6 * Q + k, R);
-                bfly(f1[3], g[3], w0d, P, R); sink.put(m, 2 * Q + k, P); sink.put(m, 6 * Q - k, R);
-                f1[0] = g[0]; f1[1] = g[1]; f1[2] = g[2]; f1[3] = g[3];
-                f2aP = f2bP; f2aR = f2bR; f2bP = nP; f2bR = nR;
-                q0 = q1; q1 = q2; q2 = q3; q3 = In;
-            }
-        } else {
-            // packed slot 0: (F[0], F[Q']) both real, Q' = Q slots of the input level
-            const int u1 = N / (L / 2), u0 = N / L;
-            const double2 w8 = tw[u1 * Q];                          // W_{8Q}^{Q}  = W_8
-            const double2 wa = tw[u0 * 2 * Q];                      // W_{16Q}^{2Q} = W_8
-            const double2 wb = tw[u0 * Q], wc = tw[u0 * 3 * Q];     // W_16, W_16^3
-            struct F2s { double r0, r2; double2 cQ; };              // idx 0, 2Q (real), Q (complex)
-            struct F1s { double s0, s4; double2 c2, c1, c3; };      // idx 0, 4Q (real), 2Q, Q, 3Q
-            auto mk2 = [](double2 A, double2 B) {
-                F2s f; f.r0 = A.x + B.x; f.r2 = A.x - B.x; f.cQ = make_double2(A.y, -B.y); return f;
-            };
-            auto mk1 = [&](const F2s& A, const F2s& B) {
-                F1s f; f.s0 = A.r0 + B.r0; f.s4 = A.r0 - B.r0; f.c2 = make_double2(A.r2, -B.r2);
-                bfly(A.cQ, B.cQ, w8, f.c1, f.c3);
-                return f;
-            };
-            double2 q0, q1, q2, q3;
-            F2s f2a, f2b;
-            F1s f1;
-            {
-                double2 I0 = WS_IN(m0), I1 = WS_IN(m0 + D), I2 = WS_IN(m0 + 2 * D);
-                q0 = WS_IN(m0 + 3 * D);
-                q1 = WS_IN(m0 + 4 * D); q2 = WS_IN(m0 + 5 * D); q3 = WS_IN(m0 + 6 * D);
-                F2s f20 = mk2(I0, q1);
-                f2a = mk2(I1, q2);
-                f2b = mk2(I2, q3);
-                f1 = mk1(f20, f2b);
-            }
-            for (int i = i0; i < i1; i++) {
-                const int m = r + i * D;
-                double2 In = WS_IN(m + 7 * D);
-                F2s n2 = mk2(q0, In);
-                F1s g = mk1(f2a, n2);
-                sink.put(m, 0, make_double2(f1.s0 + g.s0, f1.s0 - g.s0));
-                sink.put(m, 4 * Q, make_double2(f1.s4, -g.s4));
-                double2 P, R;
-                bfly(f1.c2, g.c2, wa, P, R); sink.put(m, 2 * Q, P); sink.put(m, 6 * Q, R);
-                bfly(f1.c1, g.c1, wb, P, R); sink.put(m, Q, P);     sink.put(m, 7 * Q, R);
-                bfly(f1.c3, g.c3, wc, P, R); sink.put(m, 3 * Q, P); sink.put(m, 5 * Q, R);
-                f1 = g; f2a = f2b; f2b = n2;
-                q0 = q1; q1 = q2; q2 = q3; q3 = In;
-            }
+        const int m0 = sub * per;
+        sink.bind(k);
+        double2 qa, qb, qc, qd;                  // inputs I_{m+3..m+6}
+        double2 eP, eR, oP, oR;                  // F2(m+1), F2(m+2)
+        double2 ha[4], hb[4];                    // F1(m) / F1(m+1), alternating
+        {
+            const double2 I0 = src[m0 * stride], I1 = src[(m0 + 1) * stride], I2 = src[(m0 + 2) * stride];
+            qa = src[(m0 + 3) * stride]; qb = src[(m0 + 4) * stride];
+            qc = src[(m0 + 5) * stride]; qd = src[(m0 + 6) * stride];
+            double2 zP, zR;
+            bfly(I0, qb, w2, zP, zR);            // F2(m0)
+            bfly(I1, qc, w2, eP, eR);            // F2(m0+1)
+            bfly(I2, qd, w2, oP, oR);            // F2(m0+2)
+            bfly(zP, oP, w1a, ha[0], ha[1]);     // F1(m0)
+            bfly_alt(zR, oR, w1a, ha[2], ha[3]);
         }
-#undef WS_IN
+        const double2* nxt = src + (m0 + 7) * stride;
+        for (int m = m0; m < m0 + per; m += 4) {
+            chain_step<N>(nxt, qa, eP, eR, ha, hb, w2, w1a, w0a, w0c, m, sink);
+            chain_step<N>(nxt, qb, oP, oR, hb, ha, w2, w1a, w0a, w0c, m + 1, sink);
+            chain_step<N>(nxt, qc, eP, eR, ha, hb, w2, w1a, w0a, w0c, m + 2, sink);
+            chain_step<N>(nxt, qd, oP, oR, hb, ha, w2, w1a, w0a, w0c, m + 3, sink);
+        }
+    }
+    const Tw4s ts = load_tw4s(tw, N, N, Q);
+    for (int m = tid; m < T; m += nthreads) {
+        double2 I[8], o[8];
+        int idx[8];
+        for (int j = 0; j < 8; j++) I[j] = in[(m + j) * stride];
+        radix8_special(I, ts, o);
+        slot_index8_special(Q, idx);
+        for (int j = 0; j < 8; j++) sink.put0(m, idx[j], o[j]);
     }
 }
 

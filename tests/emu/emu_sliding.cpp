@@ -12,16 +12,29 @@
 using namespace ws_slide;
 
 namespace {
+template <int N>
 struct GlobalSink {
-    double* out; int N; int64_t w0, nwin;
-    void put(int pos, int idx, double2 v) {
-        int64_t w = w0 + pos;
+    double* out; int64_t w0, nwin;
+    int k; int pos;
+    void bind(int kk) { k = kk; }
+    void begin(int p) { pos = p; }
+    template <int J> void put(double2 v) { store(pos, SlotOfs<J>::c * (N / 16) + SlotOfs<J>::sgn * k, v); }
+    void put0(int p, int i, double2 v) { if (i == 0) v.y = 0.0; store(p, i, v); }   // Nyquist dropped
+    void store(int p, int i, double2 v) {
+        int64_t w = w0 + p;
         if (w >= nwin) return;
-        double* o = out + w * N + 2 * (int64_t)idx;
-        o[0] = v.x;
-        o[1] = idx == 0 ? 0.0 : v.y;     // slot 0 carries the Nyquist bin in .y: dropped
+        double* o = out + w * N + 2 * (int64_t)i;
+        o[0] = v.x; o[1] = v.y;
     }
 };
+
+template <int N>
+void top(const Plan& pl, const std::vector<double2>& arena, const std::vector<double2>& tw, int nthreads,
+         double* out, int64_t w0, int64_t nwin) {
+    GlobalSink<N> gs{out, w0, nwin, 0, 0};
+    for (int t = 0; t < nthreads; t++)
+        chain_pass<N>(t, nthreads, arena.data() + pl.off[1], pl.T, pl.S, tw.data(), gs);
+}
 }  // namespace
 
 extern "C" int emu_sliding(const double* series, int series_len, int N, int T, int S, int nthreads,
@@ -44,13 +57,16 @@ extern "C" int emu_sliding(const double* series, int series_len, int N, int T, i
         for (int i = pl.nst; i >= 2; i--) {
             SmemSink sink{arena.data() + pl.off[i - 1], pl.stride[i - 1]};
             for (int t = 0; t < nthreads; t++)
-                fused_pass(t, nthreads, arena.data() + pl.off[i], pl.stride[i], pl.Q[i], 1 << (3 * (i - 1)),
-                           pl.P[i - 1], 1, tw.data(), N, 3 * (i - 1), sink);
+                direct_pass(t, nthreads, arena.data() + pl.off[i], pl.stride[i], pl.Q[i], 1 << (3 * (i - 1)),
+                            pl.P[i - 1], tw.data(), N, 3 * (i - 1), sink);
         }
-        GlobalSink gs{out, N, w0, nwin};
-        for (int t = 0; t < nthreads; t++)
-            fused_pass(t, nthreads, arena.data() + pl.off[1], pl.stride[1], pl.Q[1], 1, pl.T, pl.S, tw.data(),
-                       N, 0, gs);
+        switch (N) {
+            case 256: top<256>(pl, arena, tw, nthreads, out, w0, nwin); break;
+            case 512: top<512>(pl, arena, tw, nthreads, out, w0, nwin); break;
+            case 1024: top<1024>(pl, arena, tw, nthreads, out, w0, nwin); break;
+            case 2048: top<2048>(pl, arena, tw, nthreads, out, w0, nwin); break;
+            default: top<4096>(pl, arena, tw, nthreads, out, w0, nwin); break;
+        }
     }
     return 0;
 }
