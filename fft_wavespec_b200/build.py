@@ -18,6 +18,7 @@ SOURCES = [
     ("ws_abi.cu", []),
     ("ws_window_fft.cu", []),
     ("ws_sliding.cu", []),
+    ("ws_rows.cu", []),
     ("ws_inverse.cu", []),
     ("ws_series.cu", ["-fmad=false"]),
     ("ws_pla.cu", ["-fmad=false"]),

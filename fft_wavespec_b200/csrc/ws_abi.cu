@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -75,10 +76,52 @@ struct DeviceBuf {
     template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
+// Size-keyed cache of device buffers for the job table: a sliding batch job needs ~1 GB of row
+// storage, and cudaMalloc/cudaFree of that size per job (cudaFree also synchronises the device)
+// costs more than the kernel.  Buffers return to the pool in gpu_free_job and die in gpu_shutdown.
+struct DevicePool {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_list;
+    size_t cached_bytes = 0;
+    static constexpr size_t kMaxCached = (size_t)24 << 30;
+    cudaError_t get(size_t bytes, void** out) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = free_list.lower_bound(bytes);
+            if (it != free_list.end() && it->first <= bytes + bytes / 8) {
+                *out = it->second; cached_bytes -= it->first; free_list.erase(it);
+                return cudaSuccess;
+            }
+        }
+        cudaError_t e = cudaMalloc(out, bytes);
+        if (e == cudaErrorMemoryAllocation) { trim(); cudaGetLastError(); e = cudaMalloc(out, bytes); }
+        return e;
+    }
+    void put(void* p, size_t bytes) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (cached_bytes + bytes > kMaxCached) { cudaFree(p); return; }
+        free_list.emplace(bytes, p); cached_bytes += bytes;
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto& kv : free_list) cudaFree(kv.second);
+        free_list.clear(); cached_bytes = 0;
+    }
+};
+DevicePool g_pool;
+
+struct PooledBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~PooledBuf() { if (p) g_pool.put(p, bytes); }
+    cudaError_t alloc(size_t b) { bytes = b; return g_pool.get(b, &p); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
 struct Job {
     std::mutex mu;
     int kind = 0;                 // 0 single window, 1 sliding batch
-    DeviceBuf d_series, d_rows;
+    PooledBuf d_series, d_rows;
     cudaEvent_t done = nullptr;
     int64_t rows = 0;             // rows produced
     int32_t stride = 15, top_k = 0;
@@ -97,6 +140,9 @@ struct Session {
     std::map<std::pair<int, double>, std::unique_ptr<DeviceBuf>> apow;  // (N,alpha) -> alpha^j
     std::map<int64_t, std::shared_ptr<Job>> jobs;
     int64_t next_job = 1;
+    // per-stream band hand-off buffer (ws_sliding.cu -> ws_rows.cu); work on one stream is ordered,
+    // so one buffer per stream can be reused launch after launch without synchronising
+    std::map<cudaStream_t, std::unique_ptr<DeviceBuf>> band_scratch;
 };
 Session g_s;
 
@@ -284,7 +330,60 @@ int run_pipeline(const double* d_series, int32_t n_series, int32_t series_len,
             const bool plain = c->hop == 1 && c->detrend == WAVESPEC_DETREND_NONE &&
                                c->window_type == WAVESPEC_WINDOW_NONE && !p.phase;
             if (plain && ws::sliding_shared_supported(p)) {
-                WS_CUDA(ws::launch_sliding_shared(p, st), "sliding_shared kernel");
+                // Two ways to produce rows on this path: the fused in-kernel epilogue (default) or a
+                // hand-off of the in-band bins to a separate full-occupancy rows kernel
+                // (WAVESPEC_SPLIT=1).  Measured on B200 at N=1024 they are within 3 % of each
+                // other (profiles/README.md); the fused form needs no scratch and one launch.
+                static const bool split = getenv("WAVESPEC_SPLIT") != nullptr;
+                if (split && ws::rows_from_band_supported(p)) {
+                    // sliding kernel = pure streaming writer + compact band hand-off; the rows kernel
+                    // selects at full occupancy (ws_rows.cu).  The hand-off buffer is bounded: series
+                    // (and, for very long series, window ranges) are processed in chunks on one stream.
+                    const int band = p.band_hi - p.band_lo + 1;
+                    const size_t budget = (size_t)4 << 30;
+                    const size_t per_win = (size_t)band * 16;
+                    int64_t wchunk = nwin, sgroup = n_series;
+                    if (per_win * (size_t)nwin > budget) { sgroup = 1; wchunk = (int64_t)(budget / per_win); }
+                    else { sgroup = (int64_t)(budget / (per_win * (size_t)nwin)); if (sgroup > n_series) sgroup = n_series; }
+                    if (sgroup < 1) sgroup = 1;
+                    if (wchunk < 1) wchunk = 1;
+                    void* scratch = nullptr;
+                    const size_t sbytes = per_win * (size_t)wchunk * (size_t)sgroup;
+                    {
+                        std::lock_guard<std::mutex> lk(g_s.mu);
+                        auto& slot = g_s.band_scratch[st];
+                        if (!slot) slot = std::make_unique<DeviceBuf>();
+                        if (slot->bytes < sbytes) {
+                            // growing: the old buffer may still be in use by queued kernels
+                            WS_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize(band buffer)");
+                            WS_CUDA(slot->alloc(sbytes), "cudaMalloc(band buffer)");
+                        }
+                        scratch = slot->p;
+                    }
+                    int rc2 = WAVESPEC_OK;
+                    for (int64_t s0 = 0; s0 < n_series && rc2 == WAVESPEC_OK; s0 += sgroup) {
+                        const int64_t ns = (s0 + sgroup <= n_series) ? sgroup : n_series - s0;
+                        for (int64_t wa = 0; wa < nwin && rc2 == WAVESPEC_OK; wa += wchunk) {
+                            Params q = p;
+                            q.series = p.series + s0 * p.series_stride; q.n_series = (int32_t)ns;
+                            if (p.spectra) q.spectra = p.spectra + s0 * nwin * N;
+                            if (p.rows) q.rows = p.rows + s0 * nwin * p.K * p.row_stride;
+                            if (p.bins) q.bins = p.bins + s0 * nwin * p.K;
+                            if (p.waves) q.waves = p.waves + s0 * nwin * p.K;
+                            if (p.contrib) q.contrib = p.contrib + s0 * nwin * p.K;
+                            q.win_offset = wa; q.chunk_nwin = (wa + wchunk <= nwin) ? wchunk : nwin - wa;
+                            q.band_buf = static_cast<double2*>(scratch);
+                            cudaError_t e = ws::launch_sliding_shared(q, st);
+                            g_launches++;
+                            if (e == cudaSuccess) { e = ws::launch_rows_from_band(q, st); g_launches++; }
+                            if (e != cudaSuccess) rc2 = cuda_fail(e, "sliding_shared / rows_from_band kernel");
+                        }
+                    }
+                    g_launches--;      // the common increment below counts one of them
+                    if (rc2) return rc2;
+                } else {
+                    WS_CUDA(ws::launch_sliding_shared(p, st), "sliding_shared kernel");
+                }
                 g_last_kernel = "sliding_shared";
             } else {
                 WS_CUDA(ws::launch_window_fft(p, st), "window_fft kernel");
@@ -451,6 +550,8 @@ void gpu_shutdown(void) {
     cudaSetDevice(g_s.device);
     cudaDeviceSynchronize();
     g_s.jobs.clear();
+    g_s.band_scratch.clear();
+    g_pool.trim();
     g_s.tw.clear(); g_s.win.clear(); g_s.apow.clear();
     for (auto s : g_s.streams) cudaStreamDestroy(s);
     g_s.streams.clear();

@@ -38,6 +38,8 @@ struct Params {
     double* waves;             // [n_series][nwin][K] A8a, or nullptr
     double* contrib;           // [n_series][nwin][K] A8b (input of the weight-Kalman scan), or nullptr
     double* phase;             // [n_series][nwin][3][N/2], or nullptr
+    double2* band_buf;         // scratch [n_series][chunk_nwin][band]: in-band bins handed from the
+                               // sliding kernel to the rows kernel (ws_rows.cu), or nullptr
     int32_t tile_windows;      // windows per CTA tile
 };
 

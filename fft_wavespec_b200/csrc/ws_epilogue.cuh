@@ -166,10 +166,30 @@ __device__ __forceinline__ void warp_select_emit_batch(const Params& p, double* 
                 double v = pwb[e];
                 if (v > bp) { bp = v; bpos = e; }
             }
-        for (int m = Lg >> 1; m >= 1; m >>= 1) {
-            double op = shfl_xor_d(bp, m);
-            int opos = __shfl_xor_sync(0xffffffffu, bpos, m);
-            if (better(op, opos, bp, bpos)) { bp = op; bpos = opos; }
+        {
+            // Cross-lane argmax of (power desc, position asc) inside the group.  Fast path: the
+            // high word of a non-negative double orders like the double; when exactly one lane
+            // of every group holds the maximal high word that lane is the winner and is simply
+            // broadcast.  Otherwise (ties in the top 32 bits) fall back to the full comparison.
+            const int hi = (bp >= 0.0) ? __double2hiint(bp) + 1 : 0;      // 0 = no candidate
+            int mh = hi;
+            for (int m = Lg >> 1; m >= 1; m >>= 1) mh = max(mh, __shfl_xor_sync(0xffffffffu, mh, m));
+            const unsigned cand = __ballot_sync(0xffffffffu, hi == mh && mh != 0);
+            const unsigned gmask = (Lg == 32 ? 0xffffffffu : ((1u << Lg) - 1u)) << (g * Lg);
+            const unsigned mine = cand & gmask;
+            const bool unique = (mine & (mine - 1)) == 0;                 // 0 or 1 candidate
+            if (__all_sync(0xffffffffu, unique)) {
+                const int srcl = mine ? (__ffs(mine) - 1) : lane;
+                bp = __shfl_sync(0xffffffffu, bp, srcl);
+                bpos = __shfl_sync(0xffffffffu, bpos, srcl);
+                if (!mine) { bp = -1.0; bpos = 0x7fffffff; }
+            } else {
+                for (int m = Lg >> 1; m >= 1; m >>= 1) {
+                    double op = shfl_xor_d(bp, m);
+                    int opos = __shfl_xor_sync(0xffffffffu, bpos, m);
+                    if (better(op, opos, bp, bpos)) { bp = op; bpos = opos; }
+                }
+            }
         }
         if (bpos != 0x7fffffff) {
             if ((bpos & (Lg - 1)) == l) pwb[bpos] = -2.0;      // the owning lane retires it (-2 < -1)

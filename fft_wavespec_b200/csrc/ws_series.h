@@ -21,6 +21,10 @@ cudaError_t launch_window_fft(Params p, cudaStream_t stream);
 bool sliding_shared_supported(const Params& p);
 cudaError_t launch_sliding_shared(Params p, cudaStream_t stream);
 
+// ws_rows.cu
+bool rows_from_band_supported(const Params& p);
+cudaError_t launch_rows_from_band(const Params& p, cudaStream_t stream);
+
 // ws_series.cu
 cudaError_t launch_kalman4d(const double* z_base, int64_t series_stride, int64_t z_step,
                             int32_t n_series, int64_t nwin, const KalmanParams& kp, double* out,

@@ -24,6 +24,7 @@
 
 #include "ws_common.cuh"
 #include "ws_epilogue.cuh"
+#include "ws_epilogue_cta.cuh"
 #include "ws_series.h"
 #include "ws_sliding_core.cuh"
 
@@ -36,18 +37,23 @@ constexpr int kSlideThreads = 256;
 struct SlideLayout {
     int x_doubles;      // staged samples (even count)
     int arena_off;      // byte offsets inside dynamic shared memory
-    int xb_off, pw_off, stage_off, ord_off;
+    int xb_off;         // band capture [T][band] complex
+    int ov_off;         // epilogue overlay (CTA epilogue buffers, or pw + ord of the per-window path)
     int band;           // captured bins per window
-    int Lg;             // lanes per window in the batched epilogue (power of two >= K)
+    int cta_epi;        // 2: batched warp epilogue; 1: CTA-wide insertion epilogue; 0: warp-per-window path
+    int Lg;             // lanes per window of the batched warp epilogue
     int total_bytes;
 };
 
 // Receives the bins of the top pass: streams them to HBM and captures the in-band ones.
 // The eight bins of slot k are +-k + C_J Q: two moving pointers plus compile-time offsets.
-template <int N, bool SPEC, bool SEL>
+// CAP: 0 no capture, 1 capture in shared memory (fused epilogue), 2 capture to the global band
+// buffer consumed by the rows kernel
+template <int N, bool SPEC, int CAP>
 struct TopSink {
+    static constexpr bool SEL = CAP != 0;
     double2* g;             // spectra of the tile's first window
-    double2* xb;            // shared band capture
+    double2* xb;            // band capture of the tile's first window (shared or global)
     int lo, hi, band;
     int nvalid;             // windows of this tile that exist
     // per-thread state
@@ -85,7 +91,7 @@ struct TopSink {
     }
 };
 
-template <int N, bool SPEC, bool SEL>
+template <int N, bool SPEC, int CAP>
 __global__ void __launch_bounds__(kSlideThreads, 2)
 sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -115,10 +121,12 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
         __syncthreads();
     }
     // 4. top pass: level 3 -> full spectra, streamed to HBM
-    const bool want_sel = SEL;
-    TopSink<N, SPEC, SEL> top;
+    const bool want_sel = CAP == 1;
+    TopSink<N, SPEC, CAP> top;
     top.g = SPEC ? reinterpret_cast<double2*>(p.spectra) + ((int64_t)s * p.nwin + w0) * (N / 2) : nullptr;
-    top.xb = (SEL && lay.band > 0) ? reinterpret_cast<double2*>(smem_raw + lay.xb_off) : nullptr;
+    top.xb = nullptr;
+    if (CAP == 1 && lay.band > 0) top.xb = reinterpret_cast<double2*>(smem_raw + lay.xb_off);
+    if (CAP == 2) top.xb = p.band_buf + ((int64_t)s * p.chunk_nwin + (w0 - p.win_offset)) * lay.band;
     top.lo = p.band_lo; top.hi = p.band_hi; top.band = lay.band;
     if (p.select == 1 && top.lo < 1) top.lo = 1;
     if (lay.band <= 0) { top.lo = 1; top.hi = 0; }      // empty band: capture nothing
@@ -135,22 +143,32 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
         return;
     }
     const int band = lay.band, lo = top.lo;
-    double* pw = reinterpret_cast<double*>(smem_raw + lay.pw_off);
-    for (int i = tid; i < nvalid * band; i += kSlideThreads) { double2 v = top.xb[i]; pw[i] = v.x * v.x + v.y * v.y; }
-    __syncthreads();
-    if (p.select == 1) {
-        int* ord = reinterpret_cast<int*>(smem_raw + lay.ord_off) + warp * band;
-        for (int wl = warp; wl < nvalid; wl += kSlideThreads / 32) {
-            warp_select_emit(p, pw + wl * band - lo, top.xb + wl * band - lo, ord, gw_tile + wl);
-            __syncwarp();
-        }
-    } else {
-        const int wpb = 32 / lay.Lg;                                  // windows per warp batch
-        double* stage = reinterpret_cast<double*>(smem_raw + lay.stage_off) + warp * 512;
+    unsigned char* ov = smem_raw + lay.ov_off;
+    if (lay.cta_epi == 1) {
+        cta_select_emit(p, top.xb, band, lo, pl.T, nvalid, gw_tile, ov, kSlideThreads);
+        return;
+    }
+    if (lay.cta_epi == 2) {
+        // insertion rule, several windows per warp (ws_epilogue.cuh)
+        double* pwa = reinterpret_cast<double*>(ov);
+        for (int i = tid; i < nvalid * band; i += kSlideThreads) { double2 v = top.xb[i]; pwa[i] = v.x * v.x + v.y * v.y; }
+        __syncthreads();
+        const int wpb = 32 / lay.Lg;
+        double* stage = reinterpret_cast<double*>(ov + ((pl.T * band * 8 + 15) & ~15)) + warp * 512;
         for (int b0 = warp * wpb; b0 < nvalid; b0 += (kSlideThreads / 32) * wpb) {
             const int nb = (nvalid - b0) < wpb ? (nvalid - b0) : wpb;
-            warp_select_emit_batch(p, pw + b0 * band, top.xb + b0 * band, band, lo, lay.Lg, nb, gw_tile + b0, stage);
+            warp_select_emit_batch(p, pwa + b0 * band, top.xb + b0 * band, band, lo, lay.Lg, nb, gw_tile + b0, stage);
         }
+        return;
+    }
+    // selection-sort rule (A7b) or K > 8: one warp per window
+    double* pw = reinterpret_cast<double*>(ov);
+    for (int i = tid; i < nvalid * band; i += kSlideThreads) { double2 v = top.xb[i]; pw[i] = v.x * v.x + v.y * v.y; }
+    __syncthreads();
+    int* ord = reinterpret_cast<int*>(ov + pl.T * band * 8) + warp * band;
+    for (int wl = warp; wl < nvalid; wl += kSlideThreads / 32) {
+        warp_select_emit(p, pw + wl * band - lo, top.xb + wl * band - lo, ord, gw_tile + wl);
+        __syncwarp();
     }
     (void)lane;
 }
@@ -162,7 +180,7 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
         case 512:  T = 64;  S = 8;  break;
         case 1024: T = 32;  S = 4;  break;
         case 2048: T = 16;  S = 2;  break;
-        case 4096: T = 8;   S = 1;  break;
+        case 4096: T = 16;  S = 1;  break;
         default: return false;
     }
     if (const char* ov = getenv("WAVESPEC_TILE")) {       // tuning hook: "T,S"
@@ -172,34 +190,51 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
     if (!ws_slide::plan_make(pl, p.N, T, S)) return false;
     int lo = p.band_lo, hi = p.band_hi;
     if (p.select == 1 && lo < 1) lo = 1;
-    const bool sel = p.bins || p.rows || p.waves || p.contrib;
-    lay.band = (sel && hi >= lo) ? hi - lo + 1 : 0;
+    const bool sel = (p.bins || p.rows || p.waves || p.contrib) && !p.band_buf;
+    lay.band = ((sel || p.band_buf) && hi >= lo) ? hi - lo + 1 : 0;
     lay.x_doubles = (pl.x_len + 1) & ~1;
     lay.arena_off = lay.x_doubles * 8;
     const int below3 = lay.arena_off + pl.off[1] * 16;               // bytes below the level-3 array
     const int work_end = lay.arena_off + pl.arena_slots * 16;
     const int xb_bytes = pl.T * lay.band * 16;
-    // lanes per window in the batched epilogue: >= K and enough lanes that a lane scans <= 8 bins
-    int need = p.K > (lay.band + 7) / 8 ? p.K : (lay.band + 7) / 8;
-    lay.Lg = 1;
-    while (lay.Lg < need && lay.Lg < 32) lay.Lg <<= 1;
     // The band capture is written while level 3 is still being read: it may only reuse what lies
-    // below level 3, otherwise it gets its own space after the work area.  pw / stage / ord are
-    // used after the barrier that follows the top pass: they overlay the (dead) work area.
+    // below level 3, otherwise it gets its own space after the work area.  The epilogue buffers
+    // are used after the barrier that follows the top pass: they overlay the (dead) work area.
     const int warps = kSlideThreads / 32;
-    lay.xb_off = (xb_bytes <= below3) ? 0 : work_end;
-    const int xb_end = lay.xb_off + xb_bytes;
-    lay.pw_off = (lay.xb_off == 0) ? xb_bytes : 0;
-    lay.stage_off = lay.pw_off + pl.T * lay.band * 8;
-    lay.ord_off = lay.stage_off + warps * 512 * 8;
-    int end = lay.ord_off + (p.select == 1 ? warps * lay.band * 4 : 0);
-    if (lay.xb_off != 0 && end > work_end) {
-        // overlay does not fit under the capture: move the capture up
-        lay.xb_off = (end + 15) & ~15;
+    lay.cta_epi = 0;
+    lay.Lg = 32;
+    if (p.select == 0) {
+        int need = p.K > (lay.band + 7) / 8 ? p.K : (lay.band + 7) / 8;   // >= K lanes, <= 8 bins per lane
+        lay.Lg = 1;
+        while (lay.Lg < need && lay.Lg < 32) lay.Lg <<= 1;
+        lay.cta_epi = 2;
+        const char* e = getenv("WAVESPEC_EPI");                           // tuning hook
+        if (e && e[0] == 'c' && lay.band <= 128) lay.cta_epi = 1;         // rank-based CTA epilogue
     }
-    if (xb_end > end) end = xb_end;
-    if (lay.xb_off + xb_bytes > end) end = lay.xb_off + xb_bytes;
-    if (!sel) end = 0;
+    int ov_bytes;
+    if (lay.cta_epi == 2) {
+        ov_bytes = ((pl.T * lay.band * 8 + 15) & ~15) + warps * 512 * 8;
+    } else if (lay.cta_epi == 1) {
+        ov_bytes = cta_epi_layout(pl.T, lay.band, p.K, p.row_stride, p.rows != nullptr).total;
+    } else {
+        ov_bytes = pl.T * lay.band * 8 + warps * lay.band * 4;
+    }
+    ov_bytes = (ov_bytes + 15) & ~15;
+    int end;
+    if (xb_bytes <= below3) {                  // capture under level 3, overlay right after it
+        lay.xb_off = 0;
+        lay.ov_off = (xb_bytes + 15) & ~15;
+        end = lay.ov_off + ov_bytes;
+    } else if (ov_bytes <= work_end) {         // overlay on the work area, capture above it
+        lay.ov_off = 0;
+        lay.xb_off = work_end;
+        end = work_end + xb_bytes;
+    } else {                                   // overlay larger than the work area
+        lay.ov_off = 0;
+        lay.xb_off = ov_bytes;
+        end = ov_bytes + xb_bytes;
+    }
+    if (!sel || lay.band == 0) end = 0;
     lay.total_bytes = end > work_end ? end : work_end;
     lay.total_bytes = (lay.total_bytes + 15) & ~15;
     return lay.total_bytes <= 232448;
@@ -211,17 +246,17 @@ bool sliding_shared_supported(const Params& p) {
     return pick_plan(p, pl, lay);
 }
 
-template <int N, bool SPEC, bool SEL>
+template <int N, bool SPEC, int CAP>
 static cudaError_t launch_one(const Params& p, const Plan& pl, const SlideLayout& lay, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(sliding_shared_kernel<N, SPEC, SEL>,
+        cudaError_t e = cudaFuncSetAttribute(sliding_shared_kernel<N, SPEC, CAP>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     dim3 grid((unsigned)((p.chunk_nwin + pl.T - 1) / pl.T), (unsigned)p.n_series);
-    sliding_shared_kernel<N, SPEC, SEL><<<grid, kSlideThreads, lay.total_bytes, stream>>>(p, pl, lay);
+    sliding_shared_kernel<N, SPEC, CAP><<<grid, kSlideThreads, lay.total_bytes, stream>>>(p, pl, lay);
     return cudaGetLastError();
 }
 
@@ -229,9 +264,13 @@ template <int N>
 static cudaError_t launch_n(const Params& p, const Plan& pl, const SlideLayout& lay, cudaStream_t stream) {
     const bool spec = p.spectra != nullptr;
     const bool sel = p.bins || p.rows || p.waves || p.contrib;
-    if (spec && sel) return launch_one<N, true, true>(p, pl, lay, stream);
-    if (spec) return launch_one<N, true, false>(p, pl, lay, stream);
-    if (sel) return launch_one<N, false, true>(p, pl, lay, stream);
+    if (p.band_buf) {                          // hand the band to the rows kernel
+        if (spec) return launch_one<N, true, 2>(p, pl, lay, stream);
+        return launch_one<N, false, 2>(p, pl, lay, stream);
+    }
+    if (spec && sel) return launch_one<N, true, 1>(p, pl, lay, stream);
+    if (spec) return launch_one<N, true, 0>(p, pl, lay, stream);
+    if (sel) return launch_one<N, false, 1>(p, pl, lay, stream);
     return cudaSuccess;
 }
 

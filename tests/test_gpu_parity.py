@@ -445,3 +445,39 @@ def test_last_error_utf16_contract(br):
     n = br.lib().gpu_get_last_error_w(buf, 8)
     assert n == 8 and buf[7] == 0                           # truncated, terminator counted
     assert br.lib().gpu_get_last_error_w(buf, 0) == 0
+
+
+def test_split_rows_kernel_path_matches_oracle():
+    """WAVESPEC_SPLIT=1: sliding kernel hands the in-band bins to the separate rows kernel
+    (ws_rows.cu).  Run in a subprocess because the switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, numpy as np, sys
+sys.path.insert(0, ".")
+from fft_wavespec_b200 import bridge as br, synth
+from oracle import oracle as orc
+assert br.gpu_init(0, 2) == 0
+for n, extra in ((1024, 777), (512, 64), (4096, 9)):
+    s = synth.random_walk_batch(500 + n, 2, n + extra)
+    cfg = br.default_cfg(n, top_k=8, min_period=9.0, max_period=200.0)
+    out = br.OUT_SPECTRA | br.OUT_BINS | br.OUT_ROWS | br.OUT_WAVES
+    got = br.pipeline_host(s, cfg, out)
+    o = orc.PipelineCfg(); C.memmove(C.byref(o), C.byref(cfg), C.sizeof(o))
+    for i in range(2):
+        ref = orc.pipeline_series(s[i], o, out)
+        assert np.array_equal(got["bins"][i], ref["bins"])
+        assert np.abs(got["rows"][i][..., 0] - ref["rows"][..., 0]).max() <= 1e-9 * ref["rows"][..., 0].max()
+        assert np.abs(got["waves"][i] - ref["waves"]).max() <= 1e-9 * np.abs(ref["waves"]).max()
+        e = np.abs(got["spectra"][i] - ref["spectra"]).max(axis=1) / np.abs(ref["spectra"]).max(axis=1)
+        assert e.max() < 1e-9
+    rows_only = br.pipeline_host(s, cfg, br.OUT_BINS)
+    assert np.array_equal(rows_only["bins"], got["bins"])
+print("split ok", br.launch_count())
+'''
+    env = dict(os.environ, WAVESPEC_SPLIT="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "split ok" in r.stdout
