@@ -91,6 +91,8 @@ def lib():
     L.wavespec_fft_real_forward_sliding.restype = i32
     L.wavespec_pla_windows_host.argtypes = [vp, i32, i32, i32, i32, dbl, vp, vp, vp]
     L.wavespec_pla_windows_host.restype = i32
+    L.wavespec_zigzag_feed_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, dbl, i32, vp, vp]
+    L.wavespec_zigzag_feed_host.restype = i32
     L.wavespec_launch_count.argtypes = []; L.wavespec_launch_count.restype = i64
     L.wavespec_last_kernel.argtypes = []; L.wavespec_last_kernel.restype = C.c_char_p
     L.wavespec_version.argtypes = []; L.wavespec_version.restype = i32
@@ -103,7 +105,8 @@ EXPORTED_SYMBOLS = [
     "gpu_try_get_cycles", "gpu_submit_extract_cycles_batch", "gpu_try_get_cycles_batch", "gpu_free_job",
     "gpu_get_last_error_w", "gpu_fft_real_inverse", "gpu_fft_real_forward_batch",
     "wavespec_default_cfg", "wavespec_num_windows", "wavespec_pipeline_host", "wavespec_pipeline_device",
-    "wavespec_fft_real_forward_sliding", "wavespec_pla_windows_host", "wavespec_launch_count",
+    "wavespec_fft_real_forward_sliding", "wavespec_pla_windows_host", "wavespec_zigzag_feed_host",
+    "wavespec_launch_count",
     "wavespec_last_kernel", "wavespec_version",
 ]
 
@@ -267,6 +270,16 @@ def pla_windows_host(series, window_len, hop=1, max_segments=32, max_error=0.000
     _check(lib().wavespec_pla_windows_host(_ptr(x), x.size, window_len, hop, max_segments, max_error,
                                            _ptr(lines), _ptr(bounds), _ptr(counts)))
     return lines, bounds, counts
+
+
+def zigzag_feed_host(zz_main, zz_high, zz_low, window_len, hop=1, pivot_rule=0, mode=0, fallback=0.0,
+                     min_pivots=0):
+    m, h, lo = _f64(zz_main), _f64(zz_high), _f64(zz_low)
+    nw = num_windows(m.size, window_len, hop)
+    lines = np.empty((nw, window_len)); valid = np.empty(nw, dtype=np.int32)
+    _check(lib().wavespec_zigzag_feed_host(_ptr(m), _ptr(h), _ptr(lo), m.size, window_len, hop, pivot_rule, mode,
+                                           float(fallback), min_pivots, _ptr(lines), _ptr(valid)))
+    return lines, valid
 
 
 def launch_count() -> int:

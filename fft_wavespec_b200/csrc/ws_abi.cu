@@ -787,4 +787,36 @@ int32_t wavespec_pla_windows_host(const double* series, int32_t series_len, int3
     return WAVESPEC_OK;
 }
 
+int32_t wavespec_zigzag_feed_host(const double* zz_main, const double* zz_high, const double* zz_low,
+                                  int32_t series_len, int32_t window_len, int32_t hop, int32_t pivot_rule,
+                                  int32_t mode, double fallback, int32_t min_pivots, double* lines,
+                                  int32_t* valid) {
+    int rc = ensure_open();
+    if (rc) return rc;
+    if (!zz_main || !zz_high || !zz_low || !lines) return fail(WAVESPEC_BAD_ARGS, "null buffer");
+    if (window_len < 1 || hop < 1 || series_len < window_len) return fail(WAVESPEC_BAD_ARGS, "bad window/hop/series_len");
+    if (pivot_rule < 0 || pivot_rule > 1 || mode < 0 || mode > 2) return fail(WAVESPEC_BAD_ARGS, "bad pivot_rule / mode");
+    const int64_t nwin = 1 + (int64_t)(series_len - window_len) / hop;
+    const size_t sb = (size_t)series_len * 8;
+    DeviceBuf dm, dh, dl, dfb, dpv, dprev, dnext, dlines, dvalid;
+    WS_CUDA(dm.alloc(sb), "cudaMalloc"); WS_CUDA(dh.alloc(sb), "cudaMalloc"); WS_CUDA(dl.alloc(sb), "cudaMalloc");
+    WS_CUDA(dfb.alloc(8), "cudaMalloc"); WS_CUDA(dpv.alloc(sb), "cudaMalloc");
+    WS_CUDA(dprev.alloc((size_t)series_len * 4), "cudaMalloc"); WS_CUDA(dnext.alloc((size_t)series_len * 4), "cudaMalloc");
+    WS_CUDA(dlines.alloc((size_t)nwin * window_len * 8), "cudaMalloc(lines)");
+    if (valid) WS_CUDA(dvalid.alloc((size_t)nwin * 4), "cudaMalloc(valid)");
+    cudaStream_t st = pick_stream();
+    WS_CUDA(cudaMemcpyAsync(dm.p, zz_main, sb, cudaMemcpyHostToDevice, st), "H2D");
+    WS_CUDA(cudaMemcpyAsync(dh.p, zz_high, sb, cudaMemcpyHostToDevice, st), "H2D");
+    WS_CUDA(cudaMemcpyAsync(dl.p, zz_low, sb, cudaMemcpyHostToDevice, st), "H2D");
+    WS_CUDA(cudaMemcpyAsync(dfb.p, &fallback, 8, cudaMemcpyHostToDevice, st), "H2D");
+    WS_CUDA(ws::launch_zigzag(dm.as<double>(), dh.as<double>(), dl.as<double>(), dfb.as<double>(), 1, series_len,
+                              window_len, hop, pivot_rule, mode, min_pivots, dpv.as<double>(), dprev.as<int32_t>(),
+                              dnext.as<int32_t>(), dlines.as<double>(), dvalid.as<int32_t>(), st), "zigzag kernels");
+    g_launches += 2;
+    WS_CUDA(cudaMemcpyAsync(lines, dlines.p, dlines.bytes, cudaMemcpyDeviceToHost, st), "D2H lines");
+    if (valid) WS_CUDA(cudaMemcpyAsync(valid, dvalid.p, dvalid.bytes, cudaMemcpyDeviceToHost, st), "D2H valid");
+    WS_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    return WAVESPEC_OK;
+}
+
 }  // extern "C"

@@ -39,6 +39,12 @@ cudaError_t launch_pla(const double* series, int64_t series_stride, int32_t n_se
                        int32_t* seg_bounds, int32_t* seg_counts, int32_t bounds_cap,
                        cudaStream_t stream);
 
+// ws_zigzag.cu
+cudaError_t launch_zigzag(const double* zmain, const double* zhigh, const double* zlow, const double* fallback,
+                          int32_t n_series, int32_t len, int32_t N, int32_t hop, int rule, int mode, int min_pivots,
+                          double* pv, int32_t* prev, int32_t* next, double* lines, int32_t* valid,
+                          cudaStream_t stream);
+
 // ws_inverse.cu
 cudaError_t launch_inverse_real(const double* d_spec, int32_t N, int32_t n_windows, const double2* tw,
                                 double* d_out, cudaStream_t stream);

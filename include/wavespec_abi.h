@@ -220,6 +220,21 @@ WAVESPEC_API int32_t wavespec_pla_windows_host(const double* series, int32_t ser
                                                double* lines, int32_t* seg_bounds,
                                                int32_t* seg_counts);
 
+/* ZigZag pivot -> feed expansion of every window of one host series (A12).  zz_main / zz_high /
+ * zz_low are the per-bar indicator buffers in chronological order (for 1.1.0, `main` is the
+ * channel LoadWindow builds: buffer 0 where non-zero, else buffer 1 — WaveSpecZZ_1.1.0-gpuopt.mq5:
+ * 371-384).  pivot_rule 0 = 1.1.0 (:393-451: pivot where main != 0), 1 = Legacy
+ * (Legacy/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:237-262: main, else high, else low, finite).
+ * mode 0 = STEP / ALTERNATING, 1 = INTERP / CONTINUOUS, 2 = MID ((high+low)/2).
+ * fallback = value of a window without pivots ((high[0]+low[0])/2 of the chart in 1.1.0).
+ * valid[w] (may be NULL) = 1 when the window has at least min_pivots pivots (Legacy skips bars
+ * with fewer than 2, :305-306). */
+WAVESPEC_API int32_t wavespec_zigzag_feed_host(const double* zz_main, const double* zz_high,
+                                               const double* zz_low, int32_t series_len,
+                                               int32_t window_len, int32_t hop, int32_t pivot_rule,
+                                               int32_t mode, double fallback, int32_t min_pivots,
+                                               double* lines, int32_t* valid);
+
 /* Number of kernels launched by this library since gpu_init (bench.py `gpu_launches`). */
 WAVESPEC_API int64_t wavespec_launch_count(void);
 

@@ -481,3 +481,50 @@ print("split ok", br.launch_count())
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "split ok" in r.stdout
+
+
+# ---- A12 ZigZag pivot -> feed expansion ---------------------------------------------------------
+def _zigzag_buffers(n, seed, density=0.06):
+    """Synthetic stock-ZigZag buffers: sparse alternating highs/lows in `main`, high/low maps."""
+    rng = np.random.default_rng(seed)
+    close = synth.random_walk(seed, n)
+    hi, lo = synth.high_low(seed, close)
+    main = np.zeros(n); zh = np.zeros(n); zl = np.zeros(n)
+    idx = np.flatnonzero(rng.random(n) < density)
+    for c, a in enumerate(idx):
+        if c % 2 == 0:
+            main[a] = hi[a]; zh[a] = hi[a]
+        else:
+            main[a] = lo[a]; zl[a] = lo[a]
+    return main, zh, zl, hi, lo
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_zigzag_feed_110_bit_exact(br, oracle, mode):
+    n, N = 900, 256
+    main, zh, zl, hi, lo = _zigzag_buffers(n, 700 + mode)
+    main[:40] = 0.0                                        # first windows start before any pivot
+    fb = (hi[0] + lo[0]) * 0.5
+    lines, valid = br.zigzag_feed_host(main, hi, lo, N, 1, pivot_rule=0, mode=mode, fallback=fb)
+    for w in range(0, n - N + 1, 13):
+        ref = oracle.zigzag_feed_110(main[w:w + N], hi[w:w + N], lo[w:w + N], mode, hi[0], lo[0])
+        assert np.array_equal(lines[w], ref), (mode, w)
+    # a window with no pivot at all falls back to (high[0]+low[0])/2
+    empty = np.zeros(n)
+    lines, _ = br.zigzag_feed_host(empty, hi, lo, N, 7, pivot_rule=0, mode=0, fallback=fb)
+    assert np.all(lines == fb)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_zigzag_series_legacy_bit_exact(br, oracle, mode):
+    n, N = 700, 128
+    main, zh, zl, hi, lo = _zigzag_buffers(n, 710 + mode, density=0.03)
+    main[100:140] = 0.0; zh[120] = hi[120]                 # pivot visible only through the high map
+    main[300] = np.inf                                     # non-finite main value is ignored
+    lines, valid = br.zigzag_feed_host(main, zh, zl, N, 1, pivot_rule=1, mode=1 - mode, fallback=0.0,
+                                       min_pivots=2)
+    for w in range(0, n - N + 1, 9):
+        ok, ref = oracle.zigzag_series_legacy(main[w:w + N], zh[w:w + N], zl[w:w + N], mode)
+        assert bool(valid[w]) == ok, w
+        if ok:
+            assert np.array_equal(lines[w], ref), (mode, w)
