@@ -23,6 +23,13 @@ constexpr int kPlaSegCap = 60;    // segments kept per window in shared memory f
 
 struct PlaSeg { int s, e; double slope, icpt; };
 
+__device__ __forceinline__ void render_direct(const PlaSeg sg, double* line, int32_t* bounds, int q, int bounds_cap,
+                                              int N) {
+    if (line)
+        for (int i = sg.s; i <= sg.e && i < N; ++i) line[i] = sg.slope * (double)i + sg.icpt;
+    if (bounds && q < bounds_cap) { bounds[2 * q] = sg.s; bounds[2 * q + 1] = sg.e; }
+}
+
 __global__ void __launch_bounds__(32)
 pla_kernel(const double* __restrict__ series, int64_t series_stride, int64_t nwin, int32_t N,
            int32_t hop, int32_t max_segments, double max_error, double* __restrict__ lines,
@@ -37,6 +44,10 @@ pla_kernel(const double* __restrict__ series, int64_t series_stride, int64_t nwi
     const double* y = series + (int64_t)sidx * series_stride + (active ? w : 0) * hop;
 
     int count = 0;
+    bool direct = false;
+    const int64_t gw_me = (int64_t)sidx * nwin + (active ? w : 0);
+    double* line_w = lines ? lines + gw_me * N : nullptr;
+    int32_t* bounds_w = seg_bounds ? seg_bounds + gw_me * bounds_cap * 2 : nullptr;
     if (active) {
         int stk_s[kPlaStack], stk_e[kPlaStack];
         int sp = 0;
@@ -84,21 +95,38 @@ pla_kernel(const double* __restrict__ series, int64_t series_stride, int64_t nwi
                 }
             }
             if (leaf) {
-                if (count < kPlaSegCap) segs[lane][count] = PlaSeg{s, e, slope, icpt};
-                else atomicExch(overflow, 2);
+                if (count < kPlaSegCap && !direct) {
+                    segs[lane][count] = PlaSeg{s, e, slope, icpt};
+                } else {
+                    // more segments than the shared staging holds (deep left spines are not bounded
+                    // by max_segments): this window renders by itself, in append order
+                    if (!direct) {
+                        direct = true;
+                        for (int q = 0; q < count; q++) render_direct(segs[lane][q], line_w, bounds_w, q, bounds_cap, N);
+                    }
+                    render_direct(PlaSeg{s, e, slope, icpt}, line_w, bounds_w, count, bounds_cap, N);
+                }
                 ++count;
             }
         }
     }
-    seg_n[lane] = count < kPlaSegCap ? count : kPlaSegCap;
+    seg_n[lane] = direct ? -count : count;      // negative: already rendered by its own thread
     __syncwarp();
 
     // render + pivots, one window at a time, whole warp cooperating
     for (int wl = 0; wl < 32; wl++) {
         const int64_t ww = (int64_t)blockIdx.x * 32 + wl;
         if (ww >= nwin) break;
-        const int cn = seg_n[wl];
+        const int cn_raw = seg_n[wl];
         const int64_t gw = (int64_t)sidx * nwin + ww;
+        if (cn_raw < 0) {                           // direct-rendered window: only the count is left to write
+            if (seg_counts && lane == 0) seg_counts[gw] = -cn_raw;
+            if (seg_bounds)
+                for (int q = lane; q < bounds_cap; q += 32)
+                    if (q >= -cn_raw) { seg_bounds[(gw * bounds_cap + q) * 2] = -1; seg_bounds[(gw * bounds_cap + q) * 2 + 1] = -1; }
+            continue;
+        }
+        const int cn = cn_raw;
         if (lines) {
             double* line = lines + gw * N;
             for (int q = 0; q < cn; q++) {

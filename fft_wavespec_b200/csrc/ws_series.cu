@@ -36,8 +36,17 @@ __global__ void kalman4d_kernel(const double* __restrict__ z_base, int64_t serie
     double ema_prev = 0.0;
     bool ema_ready = false;
 
+    // measurements are prefetched kPre steps ahead: the recursion is a dependent FP64 chain and a
+    // global load issued at the top of each step would put its full latency on that chain
+    constexpr int kPre = 8;
+    double zq[kPre];
+#pragma unroll
+    for (int i = 0; i < kPre; i++) zq[i] = (i < nwin) ? z[(int64_t)i * z_step] : 0.0;
     for (int64_t w = 0; w < nwin; w++) {
-        const double zz = z[w * z_step];
+        const double zz = zq[0];
+#pragma unroll
+        for (int i = 0; i < kPre - 1; i++) zq[i] = zq[i + 1];
+        zq[kPre - 1] = (w + kPre < nwin) ? z[(w + kPre) * z_step] : 0.0;
         if (w == 0) {   // ResetKalmanState(first measurement)
             pos = zz; vel = kp.init_vel; acc = kp.init_acc; jerk = kp.init_jerk;
             P00 = fmax(1e-9, kp.init_var_pos); P11 = fmax(1e-9, kp.init_var_vel);
@@ -123,15 +132,38 @@ __global__ void wkalman_kernel(const double* __restrict__ contrib, const int32_t
     double wgt[kMaxTopK], cov[kMaxTopK];
     for (int i = 0; i < kMaxTopK; i++) { wgt[i] = 0.0; cov[i] = fmax(1e-6, p0); }
     const double* meas = meas_base + (int64_t)s * series_stride;
+    // inputs of the next bar are fetched while the current bar's dependent chain runs
+    // (fast path K <= 8 keeps them in registers)
+    double nv[8]; int nb[8]; double nm = 0.0;
+    const bool small = K <= 8;
+    if (small && nwin > 0) {
+        const double* cv0 = contrib + (int64_t)s * nwin * K; const int32_t* bn0 = bins + (int64_t)s * nwin * K;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { nv[k] = k < K ? cv0[k] : 0.0; nb[k] = k < K ? bn0[k] : -1; }
+        nm = meas[0];
+    }
     for (int64_t w = 0; w < nwin; w++) {
         const double* cv = contrib + ((int64_t)s * nwin + w) * K;
         const int32_t* bn = bins + ((int64_t)s * nwin + w) * K;
         double vals[kMaxTopK];
         int use = 0;
-        for (int k = 0; k < K; k++) if (bn[k] >= 0) vals[use++] = cv[k];
+        double mz;
+        if (small) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (k < K && nb[k] >= 0) vals[use++] = nv[k];
+            mz = nm;
+            if (w + 1 < nwin) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) { nv[k] = k < K ? cv[K + k] : 0.0; nb[k] = k < K ? bn[K + k] : -1; }
+                nm = meas[(w + 1) * meas_step];
+            }
+        } else {
+            for (int k = 0; k < K; k++) if (bn[k] >= 0) vals[use++] = cv[k];
+            mz = meas[w * meas_step];
+        }
         double blended = 0.0;
         if (use > 0) {
-            double residual = meas[w * meas_step];
+            double residual = mz;
             double innovation = R;
             double cov_tmp[kMaxTopK], w_tmp[kMaxTopK];
             for (int i = 0; i < use; i++) {

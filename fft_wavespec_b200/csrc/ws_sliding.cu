@@ -24,7 +24,6 @@
 
 #include "ws_common.cuh"
 #include "ws_epilogue.cuh"
-#include "ws_epilogue_cta.cuh"
 #include "ws_series.h"
 #include "ws_sliding_core.cuh"
 
@@ -40,7 +39,7 @@ struct SlideLayout {
     int xb_off;         // band capture [T][band] complex
     int ov_off;         // epilogue overlay (CTA epilogue buffers, or pw + ord of the per-window path)
     int band;           // captured bins per window
-    int cta_epi;        // 2: batched warp epilogue; 1: CTA-wide insertion epilogue; 0: warp-per-window path
+    int cta_epi;        // 2: batched warp epilogue (insertion rule); 0: warp-per-window path (sort rule)
     int Lg;             // lanes per window of the batched warp epilogue
     int total_bytes;
 };
@@ -49,7 +48,11 @@ struct SlideLayout {
 // The eight bins of slot k are +-k + C_J Q: two moving pointers plus compile-time offsets.
 // CAP: 0 no capture, 1 capture in shared memory (fused epilogue), 2 capture to the global band
 // buffer consumed by the rows kernel
-template <int N, bool SPEC, int CAP>
+// TOP: levels fused in the top pass (3: eight bins per slot, 2: four bins per slot)
+template <int J, int TOP> struct SlotOf { static constexpr int c = ws_slide::SlotOfs<J>::c, sgn = ws_slide::SlotOfs<J>::sgn; };
+template <int J> struct SlotOf<J, 2> { static constexpr int c = ws_slide::SlotOfs4<J & 3>::c, sgn = ws_slide::SlotOfs4<J & 3>::sgn; };
+
+template <int N, bool SPEC, int CAP, int TOP>
 struct TopSink {
     static constexpr bool SEL = CAP != 0;
     double2* g;             // spectra of the tile's first window
@@ -61,15 +64,18 @@ struct TopSink {
     unsigned inband;
     double2 *gpP, *gpM, *xpP, *xpM;
     bool ok;
-    static constexpr int Q = N / 16, N2 = N / 2;
+    static constexpr int Q = N >> (TOP + 1), N2 = N / 2;
     template <int J> __device__ __forceinline__ void mark() {
-        const int idx = ws_slide::SlotOfs<J>::c * Q + ws_slide::SlotOfs<J>::sgn * k;
+        const int idx = SlotOf<J, TOP>::c * Q + SlotOf<J, TOP>::sgn * k;
         if (idx >= lo && idx <= hi) inband |= 1u << J;
     }
     __device__ __forceinline__ void bind(int kk) {
         k = kk;
         inband = 0;
-        if (SEL) { mark<0>(); mark<1>(); mark<2>(); mark<3>(); mark<4>(); mark<5>(); mark<6>(); mark<7>(); }
+        if (SEL) {
+            mark<0>(); mark<1>(); mark<2>(); mark<3>();
+            if (TOP == 3) { mark<4>(); mark<5>(); mark<6>(); mark<7>(); }
+        }
     }
     __device__ __forceinline__ void begin(int m) {
         ok = m < nvalid;
@@ -78,8 +84,8 @@ struct TopSink {
     }
     template <int J> __device__ __forceinline__ void put(double2 v) {
         if (!ok) return;
-        constexpr int c = ws_slide::SlotOfs<J>::c * Q;
-        constexpr bool plus = ws_slide::SlotOfs<J>::sgn > 0;
+        constexpr int c = SlotOf<J, TOP>::c * Q;
+        constexpr bool plus = SlotOf<J, TOP>::sgn > 0;
         if (SPEC) __stcs((plus ? gpP : gpM) + c, v);
         if (SEL) if ((inband >> J) & 1u) (plus ? xpP : xpM)[c] = v;
     }
@@ -91,8 +97,8 @@ struct TopSink {
     }
 };
 
-template <int N, bool SPEC, int CAP>
-__global__ void __launch_bounds__(kSlideThreads, 2)
+template <int N, bool SPEC, int CAP, int TOP>
+__global__ void __launch_bounds__(kSlideThreads, TOP == 3 ? 2 : 3)
 sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* x = reinterpret_cast<double*>(smem_raw);
@@ -116,13 +122,13 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     // 3. chain-free radix-8 passes down to level 3
     for (int i = pl.nst; i >= 2; i--) {
         ws_slide::SmemSink sink{arena + pl.off[i - 1], pl.stride[i - 1]};
-        ws_slide::direct_pass(tid, kSlideThreads, arena + pl.off[i], pl.stride[i], pl.Q[i], 1 << (3 * (i - 1)),
-                              pl.P[i - 1], p.tw, pl.N, 3 * (i - 1), sink);
+        ws_slide::direct_pass(tid, kSlideThreads, arena + pl.off[i], pl.stride[i], pl.Q[i], 1 << pl.lev[i - 1],
+                              pl.P[i - 1], p.tw, pl.N, pl.lev[i - 1], sink);
         __syncthreads();
     }
     // 4. top pass: level 3 -> full spectra, streamed to HBM
     const bool want_sel = CAP == 1;
-    TopSink<N, SPEC, CAP> top;
+    TopSink<N, SPEC, CAP, TOP> top;
     top.g = SPEC ? reinterpret_cast<double2*>(p.spectra) + ((int64_t)s * p.nwin + w0) * (N / 2) : nullptr;
     top.xb = nullptr;
     if (CAP == 1 && lay.band > 0) top.xb = reinterpret_cast<double2*>(smem_raw + lay.xb_off);
@@ -131,7 +137,8 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     if (p.select == 1 && top.lo < 1) top.lo = 1;
     if (lay.band <= 0) { top.lo = 1; top.hi = 0; }      // empty band: capture nothing
     top.nvalid = nvalid;
-    ws_slide::chain_pass<N>(tid, kSlideThreads, arena + pl.off[1], pl.T, pl.S, p.tw, top);
+    if (TOP == 3) ws_slide::chain_pass<N>(tid, kSlideThreads, arena + pl.off[1], pl.T, pl.S, p.tw, top);
+    else ws_slide::chain_pass4<N>(tid, kSlideThreads, arena + pl.off[1], pl.T, pl.S, p.tw, top);
     if (!want_sel) return;
     __syncthreads();
     // 5. selection + rows
@@ -144,10 +151,6 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     }
     const int band = lay.band, lo = top.lo;
     unsigned char* ov = smem_raw + lay.ov_off;
-    if (lay.cta_epi == 1) {
-        cta_select_emit(p, top.xb, band, lo, pl.T, nvalid, gw_tile, ov, kSlideThreads);
-        return;
-    }
     if (lay.cta_epi == 2) {
         // insertion rule, several windows per warp (ws_epilogue.cuh)
         double* pwa = reinterpret_cast<double*>(ov);
@@ -183,11 +186,14 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
         case 4096: T = 16;  S = 1;  break;
         default: return false;
     }
-    if (const char* ov = getenv("WAVESPEC_TILE")) {       // tuning hook: "T,S"
-        int t = 0, sc = 0;
-        if (sscanf(ov, "%d,%d", &t, &sc) == 2 && t > 0 && sc > 0) { T = t; S = sc; }
+    int top = 3;
+    if (const char* ov = getenv("WAVESPEC_TILE")) {       // tuning hook: "T,S[,top]"
+        int t = 0, sc = 0, tp = 3;
+        int n = sscanf(ov, "%d,%d,%d", &t, &sc, &tp);
+        if (n >= 2 && t > 0 && sc > 0) { T = t; S = sc; }
+        if (n == 3) top = tp;
     }
-    if (!ws_slide::plan_make(pl, p.N, T, S)) return false;
+    if (!ws_slide::plan_make(pl, p.N, T, S, top)) return false;
     int lo = p.band_lo, hi = p.band_hi;
     if (p.select == 1 && lo < 1) lo = 1;
     const bool sel = (p.bins || p.rows || p.waves || p.contrib) && !p.band_buf;
@@ -208,14 +214,10 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
         lay.Lg = 1;
         while (lay.Lg < need && lay.Lg < 32) lay.Lg <<= 1;
         lay.cta_epi = 2;
-        const char* e = getenv("WAVESPEC_EPI");                           // tuning hook
-        if (e && e[0] == 'c' && lay.band <= 128) lay.cta_epi = 1;         // rank-based CTA epilogue
     }
     int ov_bytes;
     if (lay.cta_epi == 2) {
         ov_bytes = ((pl.T * lay.band * 8 + 15) & ~15) + warps * 512 * 8;
-    } else if (lay.cta_epi == 1) {
-        ov_bytes = cta_epi_layout(pl.T, lay.band, p.K, p.row_stride, p.rows != nullptr).total;
     } else {
         ov_bytes = pl.T * lay.band * 8 + warps * lay.band * 4;
     }
@@ -246,18 +248,23 @@ bool sliding_shared_supported(const Params& p) {
     return pick_plan(p, pl, lay);
 }
 
-template <int N, bool SPEC, int CAP>
-static cudaError_t launch_one(const Params& p, const Plan& pl, const SlideLayout& lay, cudaStream_t stream) {
+template <int N, bool SPEC, int CAP, int TOP>
+static cudaError_t launch_top(const Params& p, const Plan& pl, const SlideLayout& lay, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(sliding_shared_kernel<N, SPEC, CAP>,
+        cudaError_t e = cudaFuncSetAttribute(sliding_shared_kernel<N, SPEC, CAP, TOP>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     dim3 grid((unsigned)((p.chunk_nwin + pl.T - 1) / pl.T), (unsigned)p.n_series);
-    sliding_shared_kernel<N, SPEC, CAP><<<grid, kSlideThreads, lay.total_bytes, stream>>>(p, pl, lay);
+    sliding_shared_kernel<N, SPEC, CAP, TOP><<<grid, kSlideThreads, lay.total_bytes, stream>>>(p, pl, lay);
     return cudaGetLastError();
+}
+
+template <int N, bool SPEC, int CAP>
+static cudaError_t launch_one(const Params& p, const Plan& pl, const SlideLayout& lay, cudaStream_t stream) {
+    return pl.top == 3 ? launch_top<N, SPEC, CAP, 3>(p, pl, lay, stream) : launch_top<N, SPEC, CAP, 2>(p, pl, lay, stream);
 }
 
 template <int N>

@@ -37,44 +37,58 @@ static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y
 
 namespace ws_slide {
 
-// Geometry of one tile.  Level indices: 0 = full window transform; `nst` fused passes cover levels
-// 3*nst -> 0; the bottom level sb = 3*nst is computed directly from the samples (Lb-point DFT).
+// Geometry of one tile.  Level indices: 0 = full window transform.  The top pass keeps `top`
+// levels in registers (3: radix-8 chain reading level 3; 2: radix-4 chain reading level 2, half the
+// registers per thread); below it chain-free radix-8 passes connect the stored levels
+// lev[i] = top + 3 (i - 1), i = 1..nst; the deepest one, sb = lev[nst], is computed directly from
+// the samples (Lb-point DFT, Lb <= 16).
 struct Plan {
     int N, log2N;
     int T;            // windows per tile
-    int S;            // sub-chains of the top pass (T % S == 0)
-    int nst;          // fused passes: 2 (N <= 1024) or 3
-    int sb;           // bottom level = 3*nst
+    int S;            // sub-chains of the top pass (T % S == 0, (T/S) % 4 == 0)
+    int top;          // levels fused in the top pass: 3 or 2
+    int nst;          // stored levels
+    int sb;           // bottom level = lev[nst]
     int Lb;           // bottom DFT length = N >> sb  (2..16)
-    int Q[4];         // slots per vector at level 3*i : Q[i] = N >> (3*i + 1)   (Q[0] = N/2)
-    int P[4];         // positions held at level 3*i   : P[i] = T + (1 << 3*i) - 1
+    int lev[4];       // lev[i] = level index of stored level i (lev[0] = 0)
+    int Q[4];         // slots per vector at stored level i : Q[i] = N >> (lev[i] + 1)   (Q[0] = N/2)
+    int P[4];         // positions held at stored level i   : P[i] = T + (1 << lev[i]) - 1
     int stride[4];    // slots between consecutive positions in shared memory (padded)
-    int off[4];       // slot offset of level 3*i's array inside the vector arena (i >= 1)
+    int off[4];       // slot offset of stored level i inside the vector arena (i >= 1)
     int x_len;        // staged samples: T + N - 1
     int arena_slots;  // total double2 slots of the vector arena
 };
 
-WS_HD bool plan_make(Plan& pl, int N, int T, int S) {
+WS_HD int top_stride(int q) { return q >= 64 ? q : q + (q >> 3 ? (q >> 3) : 1); }
+
+WS_HD bool plan_make(Plan& pl, int N, int T, int S, int top = 3) {
     pl.N = N;
     int l = 0;
     while ((1 << l) < N) l++;
     pl.log2N = l;
     if ((1 << l) != N || N < 256 || N > 4096) return false;
-    pl.T = T; pl.S = S;
+    if (top != 2 && top != 3) return false;
+    pl.T = T; pl.S = S; pl.top = top;
     if (S < 1 || T % S || (T / S) % 4) return false;
-    pl.nst = (N <= 1024) ? 2 : 3;
-    pl.sb = 3 * pl.nst;
+    // deepest stored level: the smallest lev = top + 3 j whose direct DFT length N >> lev is <= 16
+    pl.nst = 1;
+    while ((N >> (top + 3 * (pl.nst - 1))) > 16) pl.nst++;
+    if (pl.nst > 3) return false;
+    pl.lev[0] = 0;
+    for (int i = 1; i <= pl.nst; i++) pl.lev[i] = top + 3 * (i - 1);
+    pl.sb = pl.lev[pl.nst];
     pl.Lb = N >> pl.sb;
+    if (pl.Lb < 2) return false;
     for (int i = 0; i <= pl.nst; i++) {
-        pl.Q[i] = N >> (3 * i + 1);
-        pl.P[i] = T + (1 << (3 * i)) - 1;
+        pl.Q[i] = N >> (pl.lev[i] + 1);
+        pl.P[i] = T + (1 << pl.lev[i]) - 1;
         // pad so that the 8 lanes of a quarter warp never share a bank group when they write
         // different positions (a writer pass has Q_in = q/8 slots per residue)
         int q = pl.Q[i];
-        pl.stride[i] = (i == pl.nst) ? q + 1 : (q >= 64 ? q : q + (q >> 3 ? (q >> 3) : 1));
+        pl.stride[i] = (i == pl.nst && i != 1) ? q + 1 : top_stride(q);
     }
-    // arena order: deepest level first, level 3 (read by the top pass) last, so that the
-    // epilogue buffers can reuse everything below level 3 while the top pass still reads it
+    // arena order: deepest level first, the level read by the top pass last, so that the epilogue
+    // buffers can reuse everything below it while the top pass still reads it
     int off = 0;
     for (int i = pl.nst; i >= 1; i--) { pl.off[i] = off; off += pl.P[i] * pl.stride[i]; }
     pl.off[0] = 0;
@@ -256,10 +270,11 @@ WS_HD void bfly_alt(double2 A, double2 B, double2 w, double2& P, double2& R) {
     R = make_double2(A.x - t.x, t.y - A.y);
 }
 
-template <int N> struct TopGeom {
-    static constexpr int Q = N / 16;                                  // slots of a level-3 vector
-    static constexpr int stride = Q >= 64 ? Q : Q + (Q >> 3);         // = Plan::stride[1]
+template <int N, int TOP = 3> struct TopGeomT {
+    static constexpr int Q = N >> (TOP + 1);                          // slots of a vector at level TOP
+    static constexpr int stride = Q >= 64 ? Q : Q + ((Q >> 3) ? (Q >> 3) : 1);   // = Plan::stride[1]
 };
+template <int N> using TopGeom = TopGeomT<N, 3>;
 
 template <int N, class Sink>
 WS_HD void chain_step(const double2*& nxt, double2& qold, double2& f2oP, double2& f2oR, const double2* f1,
@@ -324,6 +339,76 @@ WS_HD void chain_pass(int tid, int nthreads, const double2* in, int T, int S, co
         radix8_special(I, ts, o);
         slot_index8_special(Q, idx);
         for (int j = 0; j < 8; j++) sink.put0(m, idx[j], o[j]);
+    }
+}
+
+// ---- radix-4 top pass (levels 2 -> 0): half the register state of the radix-8 chain -------------
+// A thread owns one general slot k of level 2 (Q = N/8 slots) and a sub-chain of consecutive windows:
+// per window ONE new slot in, FOUR bins out (k, 4Q-k, 2Q-k, 2Q+k) with 3 packed butterflies; two
+// twiddles in registers (W_{N/2}^k, W_N^k; W_N^{2Q-k} = -i conj W_N^k).  Queues: inputs 2 deep,
+// level 1 one deep -> period 2, unrolled by 4.
+// Sink: as for chain_pass, with put<J>, J = 0..3 in the order k, 4Q-k, 2Q-k, 2Q+k; the packed slot 0
+// yields bins 0, Q, 2Q, 3Q per window through put0.
+template <int J> struct SlotOfs4;
+template <> struct SlotOfs4<0> { static constexpr int c = 0, sgn = +1; };
+template <> struct SlotOfs4<1> { static constexpr int c = 4, sgn = -1; };
+template <> struct SlotOfs4<2> { static constexpr int c = 2, sgn = -1; };
+template <> struct SlotOfs4<3> { static constexpr int c = 2, sgn = +1; };
+
+template <int N, class Sink>
+WS_HD void chain4_step(const double2*& nxt, double2& qold, const double2* f1, double2* g, double2 w1,
+                       double2 w0, int m, Sink& sink) {
+    const double2 In = *nxt;
+    nxt += TopGeomT<N, 2>::stride;
+    bfly(qold, In, w1, g[0], g[1]);              // F1(m+1): idx k, 2Q-k
+    qold = In;
+    double2 P, R;
+    sink.begin(m);
+    bfly(f1[0], g[0], w0, P, R);     sink.template put<0>(P); sink.template put<1>(R);
+    bfly_alt(f1[1], g[1], w0, P, R); sink.template put<2>(P); sink.template put<3>(R);   // W^{2Q-k}
+}
+
+template <int N, class Sink>
+WS_HD void chain_pass4(int tid, int nthreads, const double2* in, int T, int S, const double2* tw, Sink& sink) {
+    constexpr int Q = TopGeomT<N, 2>::Q;
+    constexpr int stride = TopGeomT<N, 2>::stride;
+    constexpr int gen = Q - 1;
+    const int per = T / S;
+    for (int c = tid; c < S * gen; c += nthreads) {
+        const int sub = c / gen, k = 1 + c - sub * gen;
+        const double2 w1 = tw[2 * k];            // W_{N/2}^k
+        const double2 w0 = tw[k];                // W_N^k
+        const double2* src = in + k;
+        const int m0 = sub * per;
+        sink.bind(k);
+        double2 qa, qb;                          // F2(m+1), F2(m+2)
+        double2 ha[2], hb[2];                    // F1(m) / F1(m+1), alternating
+        {
+            const double2 I0 = src[m0 * stride];
+            qa = src[(m0 + 1) * stride]; qb = src[(m0 + 2) * stride];
+            bfly(I0, qb, w1, ha[0], ha[1]);      // F1(m0)
+        }
+        const double2* nxt = src + (m0 + 3) * stride;
+        for (int m = m0; m < m0 + per; m += 4) {
+            chain4_step<N>(nxt, qa, ha, hb, w1, w0, m, sink);
+            chain4_step<N>(nxt, qb, hb, ha, w1, w0, m + 1, sink);
+            chain4_step<N>(nxt, qa, ha, hb, w1, w0, m + 2, sink);
+            chain4_step<N>(nxt, qb, hb, ha, w1, w0, m + 3, sink);
+        }
+    }
+    // packed slot 0 of level 2: (F2[0], F2[Q]) real -> bins 0, Q, 2Q, 3Q of every window
+    const double2 w8 = tw[Q];                    // W_N^Q = W_8
+    for (int m = tid; m < T; m += nthreads) {
+        const double2 I0 = in[m * stride], I1 = in[(m + 1) * stride], I2 = in[(m + 2) * stride], I3 = in[(m + 3) * stride];
+        // level 1 at positions m (I0, I2) and m+1 (I1, I3): idx 0, 2Q real; idx Q complex
+        const double a0 = I0.x + I2.x, a2 = I0.x - I2.x; const double2 aQ = make_double2(I0.y, -I2.y);
+        const double b0 = I1.x + I3.x, b2 = I1.x - I3.x; const double2 bQ = make_double2(I1.y, -I3.y);
+        sink.put0(m, 0, make_double2(a0 + b0, a0 - b0));      // (F[0], F[N/2]); the sink drops the Nyquist
+        sink.put0(m, 2 * Q, make_double2(a2, -b2));
+        double2 P, R;
+        bfly(aQ, bQ, w8, P, R);
+        sink.put0(m, Q, P);
+        sink.put0(m, 3 * Q, R);
     }
 }
 

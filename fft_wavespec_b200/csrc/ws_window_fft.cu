@@ -18,7 +18,7 @@
 
 namespace ws {
 
-constexpr int kThreads = 128;
+// CTA size: 128 threads, 256 for N >= 1024 (one radix-4 butterfly per thread and pass)
 
 // prologue value of sample n of a window starting at tile offset `off`
 struct Prologue {
@@ -47,6 +47,7 @@ __device__ __forceinline__ void r4_butterfly(double2& a0, double2& a1, double2& 
 // y[a] = c (x[a] + x[a-1]) + alpha y[a-1].  Blocked over the CTA: local recurrences from zero,
 // a serial carry pass over the kThreads chunk ends, then the alpha^k fix-up.  Differs from the
 // serial loop by rounding only (a few ulp of y).
+template <int kThreads>
 __device__ void cta_trend_iir(const double* x, int L, double al, double c, double* y, double* carry) {
     const int tid = threadIdx.x;
     const int chunk = (L + kThreads - 1) / kThreads;
@@ -75,6 +76,7 @@ __device__ void cta_trend_iir(const double* x, int L, double al, double c, doubl
     __syncthreads();
 }
 
+template <int kThreads>
 __global__ void __launch_bounds__(kThreads)
 window_fft_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -121,7 +123,7 @@ window_fft_kernel(const Params p) {
             double* y = scr;
             double* carry = y + Lt_max;
             const double c = p.iir_c;
-            cta_trend_iir(tile, Lt, p.iir_alpha, c, y, carry);
+            cta_trend_iir<kThreads>(tile, Lt, p.iir_alpha, c, y, carry);
             for (int t = tid; t < tw_count; t += kThreads) {
                 int a = t * p.hop;
                 delta[t] = c * (tile[a] + tile[a]) - y[a];
@@ -150,7 +152,7 @@ window_fft_kernel(const Params p) {
                 double* y = scr;
                 double* carry = y + Lt_max;
                 for (int wl = 0; wl < nw; wl++) {
-                    cta_trend_iir(tile + wl * N, N, p.iir_alpha, p.iir_c, y, carry);
+                    cta_trend_iir<kThreads>(tile + wl * N, N, p.iir_alpha, p.iir_c, y, carry);
                     for (int i = tid; i < N; i += kThreads) tile[wl * N + i] = tile[wl * N + i] - y[i];
                     __syncthreads();
                 }
@@ -316,7 +318,7 @@ window_fft_kernel(const Params p) {
 }
 
 // Host-side launcher.  Returns the dynamic shared memory it used (0 on error).
-size_t window_fft_smem_bytes(const Params& p, int tile_windows) {
+size_t window_fft_smem_bytes(const Params& p, int tile_windows, int kThreads) {
     const int N = p.N, M = N / 2;
     int q = M / 4;
     int wpc = q > 0 ? kThreads / q : kThreads;
@@ -330,7 +332,7 @@ size_t window_fft_smem_bytes(const Params& p, int tile_windows) {
     return bytes;
 }
 
-int window_fft_pick_tile(const Params& p) {
+int window_fft_pick_tile(const Params& p, int kThreads) {
     // tile sized so that the staged samples stay near 16 KB and, for the IIR detrend, fit the
     // scratch carved out of bufA (Lt <= 2*wpc*M doubles)
     const int N = p.N, M = N / 2;
@@ -350,20 +352,24 @@ int window_fft_pick_tile(const Params& p) {
     return (int)t;
 }
 
-cudaError_t launch_window_fft(Params p, cudaStream_t stream) {
-    p.tile_windows = window_fft_pick_tile(p);
-    size_t smem = window_fft_smem_bytes(p, p.tile_windows);
+template <int NT>
+static cudaError_t launch_nt(Params p, cudaStream_t stream) {
+    p.tile_windows = window_fft_pick_tile(p, NT);
+    size_t smem = window_fft_smem_bytes(p, p.tile_windows, NT);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(window_fft_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        cudaError_t e = cudaFuncSetAttribute(window_fft_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     if (smem > 232448) return cudaErrorInvalidValue;
     dim3 grid((unsigned)((p.chunk_nwin + p.tile_windows - 1) / p.tile_windows), (unsigned)p.n_series);
-    window_fft_kernel<<<grid, kThreads, smem, stream>>>(p);
+    window_fft_kernel<NT><<<grid, NT, smem, stream>>>(p);
     return cudaGetLastError();
+}
+
+cudaError_t launch_window_fft(Params p, cudaStream_t stream) {
+    return p.N >= 1024 ? launch_nt<256>(p, stream) : launch_nt<128>(p, stream);
 }
 
 }  // namespace ws

@@ -12,13 +12,16 @@
 using namespace ws_slide;
 
 namespace {
-template <int N>
+template <int N, int TOP>
 struct GlobalSink {
     double* out; int64_t w0, nwin;
     int k; int pos;
     void bind(int kk) { k = kk; }
     void begin(int p) { pos = p; }
-    template <int J> void put(double2 v) { store(pos, SlotOfs<J>::c * (N / 16) + SlotOfs<J>::sgn * k, v); }
+    template <int J> void put(double2 v) {
+        if (TOP == 3) store(pos, SlotOfs<J>::c * (N / 16) + SlotOfs<J>::sgn * k, v);
+        else store(pos, SlotOfs4<J & 3>::c * (N / 8) + SlotOfs4<J & 3>::sgn * k, v);
+    }
     void put0(int p, int i, double2 v) { if (i == 0) v.y = 0.0; store(p, i, v); }   // Nyquist dropped
     void store(int p, int i, double2 v) {
         int64_t w = w0 + p;
@@ -31,16 +34,30 @@ struct GlobalSink {
 template <int N>
 void top(const Plan& pl, const std::vector<double2>& arena, const std::vector<double2>& tw, int nthreads,
          double* out, int64_t w0, int64_t nwin) {
-    GlobalSink<N> gs{out, w0, nwin, 0, 0};
-    for (int t = 0; t < nthreads; t++)
-        chain_pass<N>(t, nthreads, arena.data() + pl.off[1], pl.T, pl.S, tw.data(), gs);
+    if (pl.top == 3) {
+        GlobalSink<N, 3> gs{out, w0, nwin, 0, 0};
+        for (int t = 0; t < nthreads; t++)
+            chain_pass<N>(t, nthreads, arena.data() + pl.off[1], pl.T, pl.S, tw.data(), gs);
+    } else {
+        GlobalSink<N, 2> gs{out, w0, nwin, 0, 0};
+        for (int t = 0; t < nthreads; t++)
+            chain_pass4<N>(t, nthreads, arena.data() + pl.off[1], pl.T, pl.S, tw.data(), gs);
+    }
 }
 }  // namespace
 
+extern "C" int emu_sliding_top(const double* series, int series_len, int N, int T, int S, int top_levels,
+                               int nthreads, double* out);
+
 extern "C" int emu_sliding(const double* series, int series_len, int N, int T, int S, int nthreads,
                            double* out) {
+    return emu_sliding_top(series, series_len, N, T, S, 3, nthreads, out);
+}
+
+extern "C" int emu_sliding_top(const double* series, int series_len, int N, int T, int S, int top_levels,
+                               int nthreads, double* out) {
     Plan pl;
-    if (!plan_make(pl, N, T, S)) return -1;
+    if (!plan_make(pl, N, T, S, top_levels)) return -1;
     const int64_t nwin = series_len - N + 1;
     if (nwin < 1) return -2;
     std::vector<double2> tw(N);
@@ -57,8 +74,8 @@ extern "C" int emu_sliding(const double* series, int series_len, int N, int T, i
         for (int i = pl.nst; i >= 2; i--) {
             SmemSink sink{arena.data() + pl.off[i - 1], pl.stride[i - 1]};
             for (int t = 0; t < nthreads; t++)
-                direct_pass(t, nthreads, arena.data() + pl.off[i], pl.stride[i], pl.Q[i], 1 << (3 * (i - 1)),
-                            pl.P[i - 1], tw.data(), N, 3 * (i - 1), sink);
+                direct_pass(t, nthreads, arena.data() + pl.off[i], pl.stride[i], pl.Q[i], 1 << pl.lev[i - 1],
+                            pl.P[i - 1], tw.data(), N, pl.lev[i - 1], sink);
         }
         switch (N) {
             case 256: top<256>(pl, arena, tw, nthreads, out, w0, nwin); break;

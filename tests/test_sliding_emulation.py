@@ -25,6 +25,8 @@ def emu():
     dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
     L.emu_sliding.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp]
     L.emu_sliding.restype = C.c_int
+    L.emu_sliding_top.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp]
+    L.emu_sliding_top.restype = C.c_int
     return L
 
 
@@ -62,3 +64,22 @@ def test_emulated_kernel_rejects_unsupported_plans(emu):
     assert emu.emu_sliding(x, 200, 128, 32, 4, 256, out) == -1      # N < 256
     assert emu.emu_sliding(x, 2000, 1024, 30, 4, 256, np.zeros((977, 1024))) == -1   # T % S != 0
     assert emu.emu_sliding(x, 2000, 1024, 8, 8, 256, np.zeros((977, 1024))) == -1    # windows per sub-chain % 4 != 0
+
+
+# radix-4 top pass (levels 2 -> 0), the low-register variant: (N, T, S)
+PLANS4 = [(256, 64, 8), (512, 32, 4), (1024, 16, 2), (1024, 32, 4), (2048, 16, 2), (4096, 8, 2), (4096, 16, 2)]
+
+
+@pytest.mark.parametrize("n,t,s", PLANS4)
+def test_emulated_radix4_top_pass_matches_oracle(emu, oracle, n, t, s):
+    for extra in (0, t - 1, 2 * t + 3):
+        x = synth.random_walk(400 + n, n + extra)
+        nw = x.size - n + 1
+        out = np.full((nw, n), np.nan)
+        assert emu.emu_sliding_top(x, x.size, n, t, s, 2, 256, out) == 0
+        assert not np.isnan(out).any(), "a bin of some window was never produced"
+        ref = np.stack([oracle.fft_interleaved(x[w:w + n]) for w in range(nw)])
+        assert (np.abs(out - ref).max(axis=1) / np.abs(ref).max(axis=1)).max() < 1e-12
+        off_dc = np.abs(out[:, 2:] - ref[:, 2:]).max(axis=1) / np.abs(ref[:, 2:]).max(axis=1)
+        assert off_dc.max() < 1e-12
+        assert np.all(out[:, 1] == 0.0)
