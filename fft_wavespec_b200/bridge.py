@@ -22,7 +22,7 @@ FEED_CLOSE, FEED_PLA = 0, 1
 DETREND_NONE, DETREND_IIR, DETREND_MEAN = 0, 1, 2
 WINDOW_NONE, WINDOW_HANN, WINDOW_HAMMING, WINDOW_BLACKMAN, WINDOW_BARTLETT, WINDOW_HANN_WIP = range(6)
 SELECT_INSERTION, SELECT_SORT = 0, 1
-OUT_SPECTRA, OUT_ROWS, OUT_BINS, OUT_WAVES, OUT_KALMAN, OUT_PHASE, OUT_WKALMAN = 1, 2, 4, 8, 16, 32, 64
+OUT_SPECTRA, OUT_ROWS, OUT_BINS, OUT_WAVES, OUT_KALMAN, OUT_PHASE, OUT_WKALMAN, OUT_TRACKER = 1, 2, 4, 8, 16, 32, 64, 128
 ROW_FIELDS = 15
 
 
@@ -42,7 +42,8 @@ class PipelineCfg(C.Structure):
         ("window_type", C.c_int32), ("select", C.c_int32), ("pla_max_segments", C.c_int32),
         ("outputs", C.c_int32), ("pla_max_error", C.c_double),
         ("wk_process_noise", C.c_double), ("wk_meas_noise", C.c_double), ("wk_init_variance", C.c_double),
-        ("kalman", Kalman4DParams)]
+        ("kalman", Kalman4DParams),
+        ("tracker_tolerance", C.c_double), ("tracker_max_inactive", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class WaveSpecError(RuntimeError):
@@ -83,9 +84,9 @@ def lib():
     L.gpu_get_last_error_w.argtypes = [C.POINTER(C.c_uint16), i32]; L.gpu_get_last_error_w.restype = i32
     L.wavespec_default_cfg.argtypes = [C.POINTER(PipelineCfg), i32]; L.wavespec_default_cfg.restype = None
     L.wavespec_num_windows.argtypes = [i32, i32, i32]; L.wavespec_num_windows.restype = i64
-    L.wavespec_pipeline_host.argtypes = [vp, i32, i32, C.POINTER(PipelineCfg)] + [vp] * 7
+    L.wavespec_pipeline_host.argtypes = [vp, i32, i32, C.POINTER(PipelineCfg)] + [vp] * 9
     L.wavespec_pipeline_host.restype = i32
-    L.wavespec_pipeline_device.argtypes = [vp, i32, i32, C.POINTER(PipelineCfg)] + [vp] * 8
+    L.wavespec_pipeline_device.argtypes = [vp, i32, i32, C.POINTER(PipelineCfg)] + [vp] * 10
     L.wavespec_pipeline_device.restype = i32
     L.wavespec_fft_real_forward_sliding.argtypes = [vp, i32, i32, i32, vp]
     L.wavespec_fft_real_forward_sliding.restype = i32
@@ -242,22 +243,25 @@ def pipeline_host(series, cfg: PipelineCfg, outputs=None):
         "kalman": np.empty((ns, nw)) if outputs & OUT_KALMAN else None,
         "phase": np.empty((ns, nw, 3, n // 2)) if outputs & OUT_PHASE else None,
         "wkalman": np.empty((ns, nw)) if outputs & OUT_WKALMAN else None,
+        "trk_index": np.empty((ns, nw, 12), dtype=np.int32) if outputs & OUT_TRACKER else None,
+        "trk_period": np.empty((ns, nw, 12)) if outputs & OUT_TRACKER else None,
     }
     st = lib().wavespec_pipeline_host(_ptr(s2), ns, sl, C.byref(cfg), _ptr(o["spectra"]), _ptr(o["rows"]),
                                       _ptr(o["bins"]), _ptr(o["waves"]), _ptr(o["kalman"]),
-                                      _ptr(o["phase"]), _ptr(o["wkalman"]))
+                                      _ptr(o["phase"]), _ptr(o["wkalman"]), _ptr(o["trk_index"]),
+                                      _ptr(o["trk_period"]))
     _check(st)
     return {k: (v[0] if squeeze else v) for k, v in o.items() if v is not None}
 
 
 def pipeline_device(d_series, n_series, series_len, cfg: PipelineCfg, spectra=0, rows=0, bins=0, waves=0,
-                    kalman=0, phase=0, wkalman=0, stream=0):
+                    kalman=0, phase=0, wkalman=0, trk_index=0, trk_period=0, stream=0):
     """Device-pointer pipeline; every buffer is a raw device address (e.g. torch.Tensor.data_ptr())."""
     vp = C.c_void_p
     st = lib().wavespec_pipeline_device(vp(d_series), n_series, series_len, C.byref(cfg), vp(spectra or None),
                                         vp(rows or None), vp(bins or None), vp(waves or None),
                                         vp(kalman or None), vp(phase or None), vp(wkalman or None),
-                                        vp(stream or None))
+                                        vp(trk_index or None), vp(trk_period or None), vp(stream or None))
     _check(st)
 
 

@@ -239,10 +239,13 @@ int validate_cfg(const wavespec_pipeline_cfg* c, int32_t series_len) {
 
 // The whole per-bar pipeline on device pointers.  Enqueues on `st`; synchronises only where a
 // temporary has to be released (PLA feed chunks, weight-Kalman inputs).
+int run_tracker_path(Params p, const wavespec_pipeline_cfg* c, int32_t* d_trk_index, double* d_trk_period,
+                     bool plain, cudaStream_t st);
+
 int run_pipeline(const double* d_series, int32_t n_series, int32_t series_len,
                  const wavespec_pipeline_cfg* c, double* d_spectra, double* d_rows, int32_t* d_bins,
                  double* d_waves, double* d_kalman, double* d_phase, double* d_wkalman,
-                 cudaStream_t st) {
+                 cudaStream_t st, int32_t* d_trk_index = nullptr, double* d_trk_period = nullptr) {
     int rc = validate_cfg(c, series_len);
     if (rc) return rc;
     if (n_series < 1 || n_series > 65535) return fail(WAVESPEC_BAD_ARGS, "n_series must be in [1, 65535]");
@@ -283,7 +286,13 @@ int run_pipeline(const double* d_series, int32_t n_series, int32_t series_len,
             p.bins = tmp_bins.as<int32_t>();
         }
     }
-    const bool any_spectral = p.spectra || p.rows || p.bins || p.waves || p.phase || p.contrib;
+    const bool want_trk = d_trk_index && d_trk_period;
+    if ((d_trk_index != nullptr) != (d_trk_period != nullptr))
+        return fail(WAVESPEC_BAD_ARGS, "tracker planes come as a pair (index and period)");
+    if (want_trk && c->feed == WAVESPEC_FEED_PLA)
+        return fail(WAVESPEC_BAD_ARGS, "the tracker plane is not wired to the PLA feed yet");
+    if (want_trk && p.band_hi < p.band_lo) return fail(WAVESPEC_BAD_ARGS, "tracker needs a non-empty band");
+    const bool any_spectral = (p.spectra || p.rows || p.bins || p.waves || p.phase || p.contrib) && !want_trk;
 
     if (c->feed == WAVESPEC_FEED_PLA) {
         // PLA lines are window-private (the recursion restarts per window): build them chunk by
@@ -391,6 +400,11 @@ int run_pipeline(const double* d_series, int32_t n_series, int32_t series_len,
             }
             g_launches++;
         }
+        if (want_trk) {
+            const bool plain = c->hop == 1 && c->detrend == WAVESPEC_DETREND_NONE &&
+                               c->window_type == WAVESPEC_WINDOW_NONE && !p.phase;
+            if ((rc = run_tracker_path(p, c, d_trk_index, d_trk_period, plain, st))) return rc;
+        }
         if (d_kalman) {
             ws::KalmanParams kp;
             std::memcpy(&kp, &c->kalman, sizeof kp);
@@ -407,6 +421,45 @@ int run_pipeline(const double* d_series, int32_t n_series, int32_t series_len,
         g_launches++;
         WS_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize(wkalman)");   // temporaries die here
     }
+    return WAVESPEC_OK;
+}
+
+// A13: FFT kernel -> compact band hand-off -> tracker kernel, chunked over windows so that the
+// hand-off buffer stays bounded; the tracker state of every series persists across chunks.
+int run_tracker_path(Params p, const wavespec_pipeline_cfg* c, int32_t* d_trk_index, double* d_trk_period,
+                     bool plain, cudaStream_t st) {
+    const int band = p.band_hi - p.band_lo + 1;
+    const int64_t nwin = p.nwin;
+    const size_t per_win = (size_t)band * 16 * (size_t)p.n_series;
+    int64_t wchunk = (int64_t)(((size_t)2 << 30) / per_win);
+    if (wchunk < 1) wchunk = 1;
+    if (wchunk > nwin) wchunk = nwin;
+    DeviceBuf scratch, states;
+    WS_CUDA(scratch.alloc(per_win * (size_t)wchunk), "cudaMalloc(band buffer)");
+    WS_CUDA(states.alloc(sizeof(ws::TrackerState) * (size_t)p.n_series), "cudaMalloc(tracker state)");
+    const bool sel = p.rows || p.bins || p.waves || p.contrib;
+    // the sliding kernel hands the band over only in its split form (insertion rule, K <= 8)
+    bool use_sliding = plain && ws::sliding_shared_supported(p) && (!sel || ws::rows_from_band_supported(p));
+    for (int64_t wa = 0; wa < nwin; wa += wchunk) {
+        Params q = p;
+        q.win_offset = wa; q.chunk_nwin = (wa + wchunk <= nwin) ? wchunk : nwin - wa;
+        q.band_buf = scratch.as<double2>();
+        if (use_sliding) {
+            WS_CUDA(ws::launch_sliding_shared(q, st), "sliding_shared kernel");
+            g_launches++;
+            if (sel) { WS_CUDA(ws::launch_rows_from_band(q, st), "rows_from_band kernel"); g_launches++; }
+            g_last_kernel = "sliding_shared";
+        } else {
+            WS_CUDA(ws::launch_window_fft(q, st), "window_fft kernel");
+            g_launches++;
+            g_last_kernel = "window_fft";
+        }
+        WS_CUDA(ws::launch_tracker(q.band_buf, p.band_lo, band, p.n_series, q.chunk_nwin, wa, nwin, p.N,
+                                   c->tracker_tolerance, c->tracker_max_inactive, states.as<ws::TrackerState>(),
+                                   d_trk_index, d_trk_period, st), "tracker kernel");
+        g_launches++;
+    }
+    WS_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize(tracker)");      // scratch dies here
     return WAVESPEC_OK;
 }
 
@@ -583,6 +636,7 @@ void wavespec_default_cfg(wavespec_pipeline_cfg* c, int32_t window_len) {
     k.adapt_gain = 0.8; k.meas_noise = 1.0; k.init_var_pos = 16.0; k.init_var_vel = 9.0;
     k.init_var_acc = 4.0; k.init_var_jerk = 1.0; k.init_vel = 0.0; k.init_acc = 0.0; k.init_jerk = 0.0;
     k.clip_std = 6.0; k.ema_blend_period = 0.0;
+    c->tracker_tolerance = 5.0; c->tracker_max_inactive = 3; c->reserved0 = 0;                    // :985-986
 }
 
 int64_t wavespec_num_windows(int32_t series_len, int32_t window_len, int32_t hop) {
@@ -593,17 +647,17 @@ int64_t wavespec_num_windows(int32_t series_len, int32_t window_len, int32_t hop
 int32_t wavespec_pipeline_device(const double* d_series, int32_t n_series, int32_t series_len,
                                  const wavespec_pipeline_cfg* cfg, double* d_spectra, double* d_rows,
                                  int32_t* d_bins, double* d_waves, double* d_kalman, double* d_phase,
-                                 double* d_wkalman, void* stream) {
+                                 double* d_wkalman, int32_t* d_trk_index, double* d_trk_period, void* stream) {
     int rc = ensure_open();
     if (rc) return rc;
     return run_pipeline(d_series, n_series, series_len, cfg, d_spectra, d_rows, d_bins, d_waves, d_kalman,
-                        d_phase, d_wkalman, static_cast<cudaStream_t>(stream));
+                        d_phase, d_wkalman, static_cast<cudaStream_t>(stream), d_trk_index, d_trk_period);
 }
 
 int32_t wavespec_pipeline_host(const double* series, int32_t n_series, int32_t series_len,
                                const wavespec_pipeline_cfg* cfg, double* spectra, double* rows,
                                int32_t* bins, double* waves, double* kalman, double* phase,
-                               double* wkalman) {
+                               double* wkalman, int32_t* trk_index, double* trk_period) {
     int rc = ensure_open();
     if (rc) return rc;
     if ((rc = validate_cfg(cfg, series_len))) return rc;
@@ -612,7 +666,7 @@ int32_t wavespec_pipeline_host(const double* series, int32_t n_series, int32_t s
     const int64_t nwin = 1 + (int64_t)(series_len - N) / cfg->hop;
     const size_t tot = (size_t)n_series * nwin;
     cudaStream_t st = pick_stream();
-    DeviceBuf ds, dsp, drw, dbn, dwv, dkl, dph, dwk;
+    DeviceBuf ds, dsp, drw, dbn, dwv, dkl, dph, dwk, dti, dtp;
     WS_CUDA(ds.alloc((size_t)n_series * series_len * 8), "cudaMalloc(series)");
     if (spectra) WS_CUDA(dsp.alloc(tot * N * 8), "cudaMalloc(spectra)");
     if (rows)    WS_CUDA(drw.alloc(tot * K * cfg->row_stride * 8), "cudaMalloc(rows)");
@@ -621,10 +675,12 @@ int32_t wavespec_pipeline_host(const double* series, int32_t n_series, int32_t s
     if (kalman)  WS_CUDA(dkl.alloc(tot * 8), "cudaMalloc(kalman)");
     if (phase)   WS_CUDA(dph.alloc(tot * 3 * (N / 2) * 8), "cudaMalloc(phase)");
     if (wkalman) WS_CUDA(dwk.alloc(tot * 8), "cudaMalloc(wkalman)");
+    if (trk_index) WS_CUDA(dti.alloc(tot * 12 * 4), "cudaMalloc(tracker index)");
+    if (trk_period) WS_CUDA(dtp.alloc(tot * 12 * 8), "cudaMalloc(tracker period)");
     WS_CUDA(cudaMemcpyAsync(ds.p, series, ds.bytes, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(series)");
     rc = run_pipeline(ds.as<double>(), n_series, series_len, cfg, dsp.as<double>(), drw.as<double>(),
                       dbn.as<int32_t>(), dwv.as<double>(), dkl.as<double>(), dph.as<double>(),
-                      dwk.as<double>(), st);
+                      dwk.as<double>(), st, dti.as<int32_t>(), dtp.as<double>());
     if (rc) { cudaStreamSynchronize(st); return rc; }
     if (spectra) WS_CUDA(cudaMemcpyAsync(spectra, dsp.p, dsp.bytes, cudaMemcpyDeviceToHost, st), "D2H spectra");
     if (rows)    WS_CUDA(cudaMemcpyAsync(rows, drw.p, drw.bytes, cudaMemcpyDeviceToHost, st), "D2H rows");
@@ -633,6 +689,8 @@ int32_t wavespec_pipeline_host(const double* series, int32_t n_series, int32_t s
     if (kalman)  WS_CUDA(cudaMemcpyAsync(kalman, dkl.p, dkl.bytes, cudaMemcpyDeviceToHost, st), "D2H kalman");
     if (phase)   WS_CUDA(cudaMemcpyAsync(phase, dph.p, dph.bytes, cudaMemcpyDeviceToHost, st), "D2H phase");
     if (wkalman) WS_CUDA(cudaMemcpyAsync(wkalman, dwk.p, dwk.bytes, cudaMemcpyDeviceToHost, st), "D2H wkalman");
+    if (trk_index) WS_CUDA(cudaMemcpyAsync(trk_index, dti.p, dti.bytes, cudaMemcpyDeviceToHost, st), "D2H tracker index");
+    if (trk_period) WS_CUDA(cudaMemcpyAsync(trk_period, dtp.p, dtp.bytes, cudaMemcpyDeviceToHost, st), "D2H tracker period");
     WS_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
     return WAVESPEC_OK;
 }
@@ -646,7 +704,7 @@ static int fft_forward_common(const double* in, int32_t window_len, int32_t hop,
     wavespec_pipeline_cfg c;
     wavespec_default_cfg(&c, window_len);
     c.hop = hop; c.outputs = WAVESPEC_OUT_SPECTRA;
-    return wavespec_pipeline_host(in, 1, series_len, &c, out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    return wavespec_pipeline_host(in, 1, series_len, &c, out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 int32_t gpu_fft_real_forward(const double* in, int32_t len, double* out) {
@@ -702,7 +760,7 @@ int32_t gpu_extract_cycles(const double* series, int32_t len, int32_t top_k, dou
     cfg_for_cycles(&c, len, 1, top_k, min_period, max_period, sample_rate_seconds, out_stride);
     if ((rc = validate_cfg(&c, len))) return rc;
     std::vector<double> rows((size_t)top_k * out_stride);
-    rc = wavespec_pipeline_host(series, 1, len, &c, nullptr, rows.data(), nullptr, nullptr, nullptr, nullptr, nullptr);
+    rc = wavespec_pipeline_host(series, 1, len, &c, nullptr, rows.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     if (rc) return rc;
     int n = top_k < out_capacity ? top_k : out_capacity;
     std::memcpy(out, rows.data(), (size_t)n * out_stride * 8);

@@ -189,6 +189,113 @@ __global__ void wkalman_kernel(const double* __restrict__ contrib, const int32_t
     }
 }
 
+// ---- A13: persistent period tracker pool + 12 stable slots -------------------------------------
+// Legacy/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:1415-1667, driven per bar as in :3450-3504.
+// One series per thread, strictly sequential over bars AND over the band candidates of a bar
+// (each UpdateTracker rewrites the period later candidates are matched against).  State lives
+// in global memory (one TrackerState per series) so that window chunks can be chained.
+// The reference quirks are kept: inactive trackers are never re-matched (:1437), erasing shifts
+// the array while the slot table keeps raw indices (:1514-1519, :1584-1589).
+__global__ void tracker_kernel(const double2* __restrict__ band, int32_t band_lo, int32_t nband,
+                               int32_t n_series, int64_t chunk_nwin, int64_t win_offset, int64_t nwin, int32_t N,
+                               double tol, int32_t max_inactive, TrackerState* __restrict__ states,
+                               int32_t* __restrict__ trk_index, double* __restrict__ trk_period) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_series) return;
+    TrackerState& st = states[s];
+    if (win_offset == 0) { st.count = 0; for (int i = 0; i < 12; i++) st.slot[i] = -1; }
+    int count = st.count;
+    for (int64_t wl = 0; wl < chunk_nwin; wl++) {
+        const double2* bw = band + ((int64_t)s * chunk_nwin + wl) * nband;
+        for (int c = 0; c < nband; c++) {
+            const int j = band_lo + c;
+            const double period = (j > 0) ? (double)N / j : 0;
+            if (period <= 0) continue;
+            const double2 x = bw[c];
+            const double power = (x.x * x.x) + (x.y * x.y);
+            int best = -1;
+            double smallest = 999999;
+            for (int i = 0; i < count; i++) {
+                if (st.bars_inactive[i] > 0) continue;
+                const double tp = st.period[i];
+                const double diff = fabs(tp - period);
+                bool same = false;
+                if (period > 0 && tp > 0) {
+                    const double d2 = fabs(period - tp);
+                    const double avg = (period + tp) / 2.0;
+                    const double pct = (d2 / avg) * 100.0;
+                    same = pct <= tol;
+                }
+                if (same && diff < smallest) { smallest = diff; best = i; }
+            }
+            if (best >= 0) {
+                st.period[best] = period; st.fft_index[best] = j; st.power[best] = power;
+                st.is_active[best] = 1; st.bars_inactive[best] = 0;
+            } else if (count < kTrackerCap) {
+                st.period[count] = period; st.fft_index[count] = j; st.power[count] = power;
+                st.is_active[count] = 1; st.bars_inactive[count] = 0;
+                count++;
+            }
+        }
+        for (int i = count - 1; i >= 0; i--) {
+            if (!st.is_active[i]) {
+                st.bars_inactive[i]++;
+                if (st.bars_inactive[i] >= max_inactive) {
+                    for (int j = i; j < count - 1; j++) {
+                        st.period[j] = st.period[j + 1]; st.power[j] = st.power[j + 1];
+                        st.fft_index[j] = st.fft_index[j + 1]; st.is_active[j] = st.is_active[j + 1];
+                        st.bars_inactive[j] = st.bars_inactive[j + 1];
+                    }
+                    count--;
+                }
+            }
+        }
+        for (int i = 0; i < count; i++) st.is_active[i] = 0;
+        // UpdateStableSlots
+        for (int q = 0; q < 12; q++) { int t = st.slot[q]; if (t < 0 || t >= count) st.slot[q] = -1; }
+        const int64_t o = ((int64_t)s * nwin + win_offset + wl) * 12;
+        int free_slots = 0;
+        for (int q = 0; q < 12; q++) {
+            int t = st.slot[q];
+            if (t >= 0) { trk_period[o + q] = st.period[t]; trk_index[o + q] = st.fft_index[t]; }
+            else free_slots++;
+        }
+        if (free_slots) {
+            // free slots take the strongest unused trackers in the order of the reference's stable
+            // descending bubble sort: larger power first, equal powers keep ascending index
+            for (int q = 0; q < 12; q++) {
+                if (st.slot[q] >= 0) continue;
+                int chosen = -1; double bp = 0.0;
+                for (int i = 0; i < count; i++) {
+                    bool used = false;
+                    for (int r = 0; r < 12; r++) used |= (st.slot[r] == i);
+                    if (used) continue;
+                    const double pw = st.power[i];
+                    if (chosen < 0 || pw > bp) { chosen = i; bp = pw; }
+                }
+                if (chosen >= 0) {
+                    st.slot[q] = chosen;
+                    trk_period[o + q] = st.period[chosen]; trk_index[o + q] = st.fft_index[chosen];
+                } else {
+                    trk_period[o + q] = 0.0; trk_index[o + q] = 0;
+                }
+            }
+        }
+    }
+    st.count = count;
+}
+
+cudaError_t launch_tracker(const double2* band, int32_t band_lo, int32_t nband, int32_t n_series,
+                           int64_t chunk_nwin, int64_t win_offset, int64_t nwin, int32_t N, double tol,
+                           int32_t max_inactive, TrackerState* states, int32_t* trk_index, double* trk_period,
+                           cudaStream_t stream) {
+    const int threads = 32;
+    tracker_kernel<<<(n_series + threads - 1) / threads, threads, 0, stream>>>(
+        band, band_lo, nband, n_series, chunk_nwin, win_offset, nwin, N, tol, max_inactive, states, trk_index,
+        trk_period);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_kalman4d(const double* z_base, int64_t series_stride, int64_t z_step,
                             int32_t n_series, int64_t nwin, const KalmanParams& kp, double* out,
                             cudaStream_t stream) {

@@ -14,6 +14,22 @@ struct KalmanParams {
     double init_vel, init_acc, init_jerk, clip_std, ema_blend_period;
 };
 
+// A13 tracker pool state of one series (ws_series.cu)
+constexpr int kTrackerCap = 512;
+struct TrackerState {
+    int32_t count;
+    int32_t slot[12];
+    double period[kTrackerCap];
+    double power[kTrackerCap];
+    int32_t fft_index[kTrackerCap];
+    int32_t is_active[kTrackerCap];
+    int32_t bars_inactive[kTrackerCap];
+};
+cudaError_t launch_tracker(const double2* band, int32_t band_lo, int32_t nband, int32_t n_series,
+                           int64_t chunk_nwin, int64_t win_offset, int64_t nwin, int32_t N, double tol,
+                           int32_t max_inactive, TrackerState* states, int32_t* trk_index, double* trk_period,
+                           cudaStream_t stream);
+
 // ws_window_fft.cu
 cudaError_t launch_window_fft(Params p, cudaStream_t stream);
 

@@ -255,6 +255,9 @@ window_fft_kernel(const Params p) {
                     p.spectra + (((int64_t)s * nwin + w0 + wb + wl)) * N);
                 g[k] = X;
             }
+            if (p.band_buf && k >= p.band_lo && k <= p.band_hi)      // hand-off to the tracker / rows kernels
+                p.band_buf[((int64_t)s * p.chunk_nwin + (w0 - p.win_offset) + wb + wl) * (p.band_hi - p.band_lo + 1) +
+                           (k - p.band_lo)] = X;
         }
         __syncthreads();
         double* pw = reinterpret_cast<double*>(in);    // Z is dead: wpc*M double2 = room for M doubles per window

@@ -156,7 +156,9 @@ enum {
     WAVESPEC_OUT_WAVES   = 8,   /* nwin * top_k doubles: A8a last-sample reconstruction */
     WAVESPEC_OUT_KALMAN  = 16,  /* nwin doubles: StepKalman4D on the newest window sample */
     WAVESPEC_OUT_PHASE   = 32,  /* nwin * 3 * window_len/2 doubles: phase, unwrapped, group delay */
-    WAVESPEC_OUT_WKALMAN = 64   /* nwin doubles: weight-Kalman blend (1.0.4-kalman.mq5:194-231) */
+    WAVESPEC_OUT_WKALMAN = 64,  /* nwin doubles: weight-Kalman blend (1.0.4-kalman.mq5:194-231) */
+    WAVESPEC_OUT_TRACKER = 128  /* nwin * 12 int32 bins + nwin * 12 double periods: the stable slots of
+                                   the period tracker pool (Legacy/...-kalman-fast.mq5:1415-1667)  */
 };
 
 /* Kalman4D parameters, defaults of Legacy/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:885-901 */
@@ -182,6 +184,9 @@ typedef struct wavespec_pipeline_cfg {
     double  pla_max_error;     /* default 0.0005                                           */
     double  wk_process_noise, wk_meas_noise, wk_init_variance; /* weight-Kalman Q, R, P0    */
     wavespec_kalman4d_params kalman;
+    double  tracker_tolerance;     /* InpTrackerTolerance, % (default 5.0)                    */
+    int32_t tracker_max_inactive;  /* InpMaxInactiveBars (default 3)                          */
+    int32_t reserved0;
 } wavespec_pipeline_cfg;
 
 /* Fills cfg with the reference defaults for a given window length. */
@@ -197,7 +202,7 @@ WAVESPEC_API int32_t wavespec_pipeline_host(const double* series, int32_t n_seri
                                             int32_t series_len, const wavespec_pipeline_cfg* cfg,
                                             double* spectra, double* rows, int32_t* bins,
                                             double* waves, double* kalman, double* phase,
-                                            double* wkalman);
+                                            double* wkalman, int32_t* trk_index, double* trk_period);
 
 /* Device-pointer pipeline (all pointers are device memory on the session's device); enqueues on
  * `stream` and returns without synchronising.  Used by bench.py (`value`) and the GPU tests. */
@@ -205,7 +210,8 @@ WAVESPEC_API int32_t wavespec_pipeline_device(const double* d_series, int32_t n_
                                               int32_t series_len, const wavespec_pipeline_cfg* cfg,
                                               double* d_spectra, double* d_rows, int32_t* d_bins,
                                               double* d_waves, double* d_kalman, double* d_phase,
-                                              double* d_wkalman, void* stream);
+                                              double* d_wkalman, int32_t* d_trk_index,
+                                              double* d_trk_period, void* stream);
 
 /* Sliding variant of gpu_fft_real_forward_batch (hop-spaced overlapping windows of one host
  * series) — named distinctly, as SURVEY.md section 8b requires. */

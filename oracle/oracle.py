@@ -31,11 +31,18 @@ class PipelineCfg(C.Structure):
         ("window_type", C.c_int32), ("select", C.c_int32), ("pla_max_segments", C.c_int32),
         ("outputs", C.c_int32), ("pla_max_error", C.c_double),
         ("wk_process_noise", C.c_double), ("wk_meas_noise", C.c_double), ("wk_init_variance", C.c_double),
-        ("kalman", Kalman4DParams)]
+        ("kalman", Kalman4DParams),
+        ("tracker_tolerance", C.c_double), ("tracker_max_inactive", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class WKalmanState(C.Structure):
     _fields_ = [("weights", C.c_double * 32), ("cov", C.c_double * 32)]
+
+
+class TrackerState(C.Structure):
+    _fields_ = [("count", C.c_int), ("period", C.c_double * 512), ("power", C.c_double * 512),
+                ("fft_index", C.c_int * 512), ("is_active", C.c_int * 512), ("bars_inactive", C.c_int * 512),
+                ("slot", C.c_int * 12)]
 
 
 def build(force: bool = False) -> str:
@@ -81,8 +88,12 @@ def lib():
     L.oracle_zigzag_feed_110.argtypes = [_dp, _dp, _dp, C.c_int, C.c_int, C.c_double, C.c_double, _dp]
     L.oracle_zigzag_series_legacy.argtypes = [_dp, _dp, _dp, C.c_int, C.c_int, _dp]
     L.oracle_zigzag_series_legacy.restype = C.c_int
+    L.oracle_tracker_reset.argtypes = [C.POINTER(TrackerState)]
+    L.oracle_tracker_step.argtypes = [C.POINTER(TrackerState), _dp, C.c_int, C.c_double, C.c_double, C.c_double,
+                                      C.c_int, _ip, _dp]
     L.oracle_default_cfg.argtypes = [C.POINTER(PipelineCfg), C.c_int]
     L.oracle_pipeline_series.argtypes = [_dp, C.c_int, C.POINTER(PipelineCfg)] + [C.c_void_p] * 7
+    L.oracle_pipeline_series_trk.argtypes = [_dp, C.c_int, C.POINTER(PipelineCfg)] + [C.c_void_p] * 9
     L.oracle_pipeline_batch_mt.argtypes = [_dp, C.c_int, C.c_int, C.POINTER(PipelineCfg), C.c_int,
                                            C.c_int64] + [C.c_void_p] * 4
     L.oracle_pipeline_batch_mt.restype = C.c_int64
@@ -195,6 +206,24 @@ def zigzag_series_legacy(zz_main, zz_high, zz_low, mode):
     return bool(ok), out
 
 
+class Tracker:
+    """Period tracker pool + 12 stable slots (A13), one bar at a time."""
+
+    def __init__(self):
+        self.st = TrackerState()
+        lib().oracle_tracker_reset(C.byref(self.st))
+
+    def step(self, spectrum, n, min_period, max_period, tol=5.0, max_inactive=3):
+        idx = np.zeros(12, dtype=np.int32); per = np.zeros(12)
+        lib().oracle_tracker_step(C.byref(self.st), _f64(spectrum), n, float(min_period), float(max_period),
+                                  float(tol), int(max_inactive), idx, per)
+        return idx, per
+
+    def trackers(self):
+        c = self.st.count
+        return [(self.st.fft_index[i], self.st.period[i], self.st.power[i], self.st.bars_inactive[i]) for i in range(c)]
+
+
 def default_cfg(window_len, **over):
     cfg = PipelineCfg()
     lib().oracle_default_cfg(C.byref(cfg), int(window_len))
@@ -203,7 +232,7 @@ def default_cfg(window_len, **over):
     return cfg
 
 
-OUT_SPECTRA, OUT_ROWS, OUT_BINS, OUT_WAVES, OUT_KALMAN, OUT_PHASE, OUT_WKALMAN = 1, 2, 4, 8, 16, 32, 64
+OUT_SPECTRA, OUT_ROWS, OUT_BINS, OUT_WAVES, OUT_KALMAN, OUT_PHASE, OUT_WKALMAN, OUT_TRACKER = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 def _ptr(a):
@@ -228,10 +257,13 @@ def pipeline_series(series, cfg, outputs=None):
         "kalman": np.zeros(nw) if outputs & OUT_KALMAN else None,
         "phase": np.zeros((nw, 3, n // 2)) if outputs & OUT_PHASE else None,
         "wkalman": np.zeros(nw) if outputs & OUT_WKALMAN else None,
+        "trk_index": np.zeros((nw, 12), dtype=np.int32) if outputs & OUT_TRACKER else None,
+        "trk_period": np.zeros((nw, 12)) if outputs & OUT_TRACKER else None,
     }
-    lib().oracle_pipeline_series(s, s.size, C.byref(cfg), _ptr(o["spectra"]), _ptr(o["rows"]),
-                                 _ptr(o["bins"]), _ptr(o["waves"]), _ptr(o["kalman"]),
-                                 _ptr(o["phase"]), _ptr(o["wkalman"]))
+    lib().oracle_pipeline_series_trk(s, s.size, C.byref(cfg), _ptr(o["spectra"]), _ptr(o["rows"]),
+                                     _ptr(o["bins"]), _ptr(o["waves"]), _ptr(o["kalman"]),
+                                     _ptr(o["phase"]), _ptr(o["wkalman"]), _ptr(o["trk_index"]),
+                                     _ptr(o["trk_period"]))
     return {k: v for k, v in o.items() if v is not None}
 
 

@@ -550,6 +550,107 @@ int oracle_zigzag_series_legacy(const double* zz_main, const double* zz_high, co
 }
 
 // ---------------------------------------------------------------------------------------------
+// A13 L/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:1415-1667, bar-loop driver :3450-3504
+void oracle_tracker_reset(oracle_tracker_state* st) {      // first-run reset, :3245-3251
+    st->count = 0;
+    for (int s = 0; s < 12; s++) st->slot[s] = -1;
+}
+
+namespace {
+bool same_period(double p1, double p2, double tol) {       // IsSamePeriod :1418-1427
+    if (p1 <= 0 || p2 <= 0) return false;
+    double diff = std::fabs(p1 - p2);
+    double avg = (p1 + p2) / 2.0;
+    double diff_pct = (diff / avg) * 100.0;
+    return diff_pct <= tol;
+}
+int find_closest(const oracle_tracker_state* st, double period, double tol) {   // :1433-1456
+    int best = -1;
+    double smallest = 999999;
+    for (int i = 0; i < st->count; i++) {
+        if (st->bars_inactive[i] > 0) continue;
+        double diff = std::fabs(st->period[i] - period);
+        if (same_period(period, st->period[i], tol)) {
+            if (diff < smallest) { smallest = diff; best = i; }
+        }
+    }
+    return best;
+}
+}  // namespace
+
+void oracle_tracker_step(oracle_tracker_state* st, const double* spectrum, int n, double min_period,
+                         double max_period, double tolerance_pct, int max_inactive_bars,
+                         int32_t* slot_index, double* slot_period) {
+    const int spectrum_size = n / 2;
+    int min_index = (int)std::ceil((double)n / max_period);
+    int max_index = (int)std::floor((double)n / min_period);
+    // 4c/5: every band bin ascending, match-or-add (:3450-3499)
+    for (int j = min_index; j <= max_index && j < spectrum_size; j++) {
+        double period = (j > 0) ? (double)n / j : 0;
+        if (period <= 0) continue;
+        double power = spectrum[j];
+        int t = find_closest(st, period, tolerance_pct);
+        if (t >= 0) {                                       // UpdateTracker :1461-1471
+            st->period[t] = period; st->fft_index[t] = j; st->power[t] = power;
+            st->is_active[t] = 1; st->bars_inactive[t] = 0;
+        } else if (st->count < ORACLE_TRACKER_CAP) {        // AddTracker :1476-1498
+            int c = st->count++;
+            st->period[c] = period; st->fft_index[c] = j; st->power[c] = power;
+            st->is_active[c] = 1; st->bars_inactive[c] = 0;
+        }
+    }
+    // DeactivateUnseenTrackers :1504-1529
+    for (int i = st->count - 1; i >= 0; i--) {
+        if (!st->is_active[i]) {
+            st->bars_inactive[i]++;
+            if (st->bars_inactive[i] >= max_inactive_bars) {
+                for (int j = i; j < st->count - 1; j++) {
+                    st->period[j] = st->period[j + 1]; st->power[j] = st->power[j + 1];
+                    st->fft_index[j] = st->fft_index[j + 1]; st->is_active[j] = st->is_active[j + 1];
+                    st->bars_inactive[j] = st->bars_inactive[j + 1];
+                }
+                st->count--;
+            }
+        }
+    }
+    for (int i = 0; i < st->count; i++) st->is_active[i] = 0;
+    // UpdateStableSlots :1582-1667
+    for (int s = 0; s < 12; s++) {
+        int t = st->slot[s];
+        if (t < 0 || t >= st->count) st->slot[s] = -1;
+    }
+    std::vector<int> sorted(st->count), used(st->count, 0);
+    for (int i = 0; i < st->count; i++) sorted[i] = i;
+    for (int i = 0; i < st->count - 1; i++)
+        for (int j = 0; j < st->count - i - 1; j++)
+            if (st->power[sorted[j]] < st->power[sorted[j + 1]]) { int t = sorted[j]; sorted[j] = sorted[j + 1]; sorted[j + 1] = t; }
+    for (int s = 0; s < 12; s++) {
+        int t = st->slot[s];
+        if (t >= 0 && t < st->count) {
+            used[t] = 1;
+            slot_period[s] = st->period[t]; slot_index[s] = st->fft_index[t];
+        }
+    }
+    for (int s = 0; s < 12; s++) {
+        if (st->slot[s] >= 0 && st->slot[s] < st->count) continue;
+        int chosen = -1;
+        for (int k = 0; k < st->count; k++) {
+            int idx = sorted[k];
+            if (used[idx]) continue;
+            chosen = idx;
+            break;
+        }
+        if (chosen != -1) {
+            st->slot[s] = chosen; used[chosen] = 1;
+            slot_period[s] = st->period[chosen]; slot_index[s] = st->fft_index[chosen];
+        } else {
+            st->slot[s] = -1;
+            slot_period[s] = 0.0; slot_index[s] = 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Pipelines (bar loops).  Stage order follows L/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:3301-3460;
 // the nodetrend/top-8/reconstruction tail follows L/...-gpuopt-nodetrend.mq5:515-568; the
 // weight-Kalman tail follows L/WaveSpecZZ_1.0.4-kalman.mq5:254-286.
@@ -562,6 +663,7 @@ void oracle_default_cfg(oracle_pipeline_cfg* cfg, int window_len) {
     cfg->outputs = 1 | 2 | 4;
     cfg->wk_process_noise = 0.25; cfg->wk_meas_noise = 9.0; cfg->wk_init_variance = 25.0;
     oracle_kalman4d_defaults(&cfg->kalman);
+    cfg->tracker_tolerance = 5.0; cfg->tracker_max_inactive = 3; cfg->reserved0 = 0;   // :985-986
 }
 
 namespace {
@@ -602,7 +704,8 @@ void fill_row(double* row, int stride, int n, int bin, double power, double re, 
 void process_window(const double* series, int64_t w, const oracle_pipeline_cfg* cfg, WinScratch& s,
                     oracle_kalman4d_state* kst, oracle_wkalman_state* wk,
                     double* spectra, double* rows, int32_t* bins, double* waves, double* kalman,
-                    double* phase, double* wkalman) {
+                    double* phase, double* wkalman, oracle_tracker_state* trk = nullptr,
+                    int32_t* trk_index = nullptr, double* trk_period = nullptr) {
     const int n = cfg->window_len;
     const int K = cfg->top_k;
     const double* src = series + w * cfg->hop;
@@ -642,6 +745,9 @@ void process_window(const double* series, int64_t w, const oracle_pipeline_cfg* 
         for (int k = 0; k < n / 2; k++) { o[2 * k] = s.re[k]; o[2 * k + 1] = s.im[k]; }
     }
     oracle_power(s.re.data(), s.im.data(), n, s.spec.data());
+    if (trk && trk_index && trk_period)
+        oracle_tracker_step(trk, s.spec.data(), n, cfg->min_period, cfg->max_period, cfg->tracker_tolerance,
+                            cfg->tracker_max_inactive, trk_index + w * 12, trk_period + w * 12);
     // 5. selection
     int sel_bin[32]; double sel_pow[32];
     for (int i = 0; i < 32; i++) { sel_bin[i] = -1; sel_pow[i] = -1.0; }
@@ -694,14 +800,25 @@ void process_window(const double* series, int64_t w, const oracle_pipeline_cfg* 
 void oracle_pipeline_series(const double* series, int series_len, const oracle_pipeline_cfg* cfg,
                             double* spectra, double* rows, int32_t* bins, double* waves,
                             double* kalman, double* phase, double* wkalman) {
+    oracle_pipeline_series_trk(series, series_len, cfg, spectra, rows, bins, waves, kalman, phase, wkalman,
+                               nullptr, nullptr);
+}
+
+void oracle_pipeline_series_trk(const double* series, int series_len, const oracle_pipeline_cfg* cfg,
+                                double* spectra, double* rows, int32_t* bins, double* waves,
+                                double* kalman, double* phase, double* wkalman,
+                                int32_t* trk_index, double* trk_period) {
     const int n = cfg->window_len;
     if (series_len < n) return;
     const int64_t nwin = 1 + (int64_t)(series_len - n) / cfg->hop;
     WinScratch s(n);
     oracle_kalman4d_state kst; std::memset(&kst, 0, sizeof kst);
     oracle_wkalman_state wk; oracle_wkalman_reset(&wk, cfg->wk_init_variance);
+    std::vector<oracle_tracker_state> trk(1);
+    oracle_tracker_reset(&trk[0]);
     for (int64_t w = 0; w < nwin; w++)
-        process_window(series, w, cfg, s, &kst, &wk, spectra, rows, bins, waves, kalman, phase, wkalman);
+        process_window(series, w, cfg, s, &kst, &wk, spectra, rows, bins, waves, kalman, phase, wkalman,
+                       &trk[0], trk_index, trk_period);
 }
 
 int64_t oracle_pipeline_batch_mt(const double* series, int n_series, int series_len,

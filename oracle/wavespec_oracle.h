@@ -101,6 +101,27 @@ void oracle_zigzag_feed_110(const double* main_ch, const double* high_ch, const 
 int oracle_zigzag_series_legacy(const double* zz_main, const double* zz_high, const double* zz_low,
                                 int n, int mode, double* price_data);
 
+/* A13 L/...-kalman-fast.mq5:1415-1667 persistent period tracker pool + 12 stable slots, driven per
+ * bar as in :3450-3504: candidates = every band bin ascending (period = N / bin), match against the
+ * closest ACTIVE tracker within `tolerance_pct` else append, deactivate / erase unseen trackers
+ * (erase shifts the array; slot indices are NOT remapped — reproduced), refill free slots by
+ * descending power (bubble sort with '<', stable). */
+#define ORACLE_TRACKER_CAP 512
+typedef struct oracle_tracker_state {
+    int count;
+    double period[ORACLE_TRACKER_CAP];
+    double power[ORACLE_TRACKER_CAP];
+    int fft_index[ORACLE_TRACKER_CAP];
+    int is_active[ORACLE_TRACKER_CAP];
+    int bars_inactive[ORACLE_TRACKER_CAP];
+    int slot[12];
+} oracle_tracker_state;
+void oracle_tracker_reset(oracle_tracker_state* st);
+/* spectrum: n/2 powers of this bar; writes the 12 slots (index 0 / period 0.0 when empty). */
+void oracle_tracker_step(oracle_tracker_state* st, const double* spectrum, int n, double min_period,
+                         double max_period, double tolerance_pct, int max_inactive_bars,
+                         int32_t* slot_index, double* slot_period);
+
 /* ---- per-series pipelines (bar loops), used by parity tests and the timed CPU baseline ---- */
 typedef struct oracle_pipeline_cfg {
     int window_len, hop, top_k, row_stride;
@@ -111,6 +132,9 @@ typedef struct oracle_pipeline_cfg {
     double pla_max_error;
     double wk_process_noise, wk_meas_noise, wk_init_variance;
     oracle_kalman4d_params kalman;
+    double tracker_tolerance;      /* InpTrackerTolerance, default 5.0 (%)  */
+    int tracker_max_inactive;      /* InpMaxInactiveBars, default 3          */
+    int reserved0;
 } oracle_pipeline_cfg;   /* field-for-field the same as wavespec_pipeline_cfg */
 
 void oracle_default_cfg(oracle_pipeline_cfg* cfg, int window_len);
@@ -121,6 +145,11 @@ void oracle_default_cfg(oracle_pipeline_cfg* cfg, int window_len);
 void oracle_pipeline_series(const double* series, int series_len, const oracle_pipeline_cfg* cfg,
                             double* spectra, double* rows, int32_t* bins, double* waves,
                             double* kalman, double* phase, double* wkalman);
+/* same, plus the tracker planes: trk_index [nwin][12] int32, trk_period [nwin][12] double */
+void oracle_pipeline_series_trk(const double* series, int series_len, const oracle_pipeline_cfg* cfg,
+                                double* spectra, double* rows, int32_t* bins, double* waves,
+                                double* kalman, double* phase, double* wkalman,
+                                int32_t* trk_index, double* trk_period);
 
 /* n_series series (row-major), split over `threads` std::threads by series then by bar range;
  * only the stateless planes (spectra/rows/bins/waves) may be requested with bar-range splits.

@@ -23,7 +23,7 @@ CASES = {
            orc.OUT_SPECTRA | orc.OUT_BINS | orc.OUT_ROWS | orc.OUT_WAVES, (0, 38, 76)),
     "c3": (2, 2048 + 40, dict(window_len=2048, top_k=8, min_period=18.0, max_period=52.0, detrend=1,
                               trend_period=1024.0, window_type=3),
-           orc.OUT_SPECTRA | orc.OUT_BINS | orc.OUT_KALMAN, (0, 40)),
+           orc.OUT_SPECTRA | orc.OUT_BINS | orc.OUT_KALMAN | orc.OUT_TRACKER, (0, 40)),
     "c4": (3, 1024 + 60, dict(window_len=1024, top_k=8, min_period=12.0, max_period=256.0, window_type=1, select=1),
            orc.OUT_SPECTRA | orc.OUT_BINS | orc.OUT_WAVES | orc.OUT_WKALMAN | orc.OUT_PHASE, (0, 60)),
     "c5": (4, 4096 + 12, dict(window_len=4096, top_k=4, min_period=9.0, max_period=200.0),

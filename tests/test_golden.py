@@ -54,6 +54,9 @@ def test_cuda_matches_golden(name):
     assert (np.abs(sp - ref).max(axis=1) / np.abs(ref).max(axis=1)).max() < 1e-9
     if f"{name}_kalman" in G.files:
         assert np.array_equal(got["kalman"], G[f"{name}_kalman"])
+    if f"{name}_trk_index" in G.files:
+        assert np.array_equal(got["trk_index"], G[f"{name}_trk_index"])
+        assert np.array_equal(got["trk_period"], G[f"{name}_trk_period"])
     if f"{name}_waves" in G.files:
         w = G[f"{name}_waves"]
         assert np.abs(got["waves"] - w).max() <= 1e-9 * np.abs(w).max()

@@ -528,3 +528,33 @@ def test_zigzag_series_legacy_bit_exact(br, oracle, mode):
         assert bool(valid[w]) == ok, w
         if ok:
             assert np.array_equal(lines[w], ref), (mode, w)
+
+
+# ---- A13 tracker pool + stable slots ------------------------------------------------------------
+@pytest.mark.parametrize("case", ["c3", "plain", "plain_rows", "wide"])
+def test_tracker_pool_slots_match_oracle(br, oracle, case):
+    if case == "c3":
+        n, over = 2048, dict(min_period=18.0, max_period=52.0, detrend=br.DETREND_IIR, trend_period=1024.0,
+                             window_type=br.WINDOW_BLACKMAN)
+        out = br.OUT_TRACKER | br.OUT_BINS
+    elif case == "plain":
+        n, over = 1024, dict(min_period=18.0, max_period=200.0)
+        out = br.OUT_TRACKER
+    elif case == "plain_rows":
+        n, over = 1024, dict(min_period=18.0, max_period=200.0)
+        out = br.OUT_TRACKER | br.OUT_ROWS | br.OUT_BINS | br.OUT_SPECTRA
+    else:
+        n, over = 256, dict(min_period=4.0, max_period=64.0, window_type=br.WINDOW_HANN, tracker_tolerance=1.0,
+                            tracker_max_inactive=2)
+        out = br.OUT_TRACKER
+    s = synth.random_walk_batch(900, 2, n + 260)
+    cfg = br.default_cfg(n, **over)
+    got = br.pipeline_host(s, cfg, out)
+    for i in range(2):
+        ref = oracle.pipeline_series(s[i], ocfg_from(oracle, cfg), out)
+        assert np.array_equal(got["trk_index"][i], ref["trk_index"]), case
+        assert np.array_equal(got["trk_period"][i], ref["trk_period"]), case
+        if "bins" in ref:
+            assert np.array_equal(got["bins"][i], ref["bins"])
+        if "rows" in ref:
+            assert np.abs(got["rows"][i][..., 0] - ref["rows"][..., 0]).max() <= REL_TOL * ref["rows"][..., 0].max()

@@ -290,6 +290,46 @@ def test_zigzag_series_legacy_modes(oracle):
     assert not ok
 
 
+# ---- A13 tracker pool, Legacy/...-kalman-fast.mq5:1415-1667 -------------------------------------
+def test_tracker_first_bar_drags_one_tracker_through_close_bins(oracle):
+    """Neighbouring bins within 5 % of each other keep updating the SAME tracker (UpdateTracker
+    rewrites the period later candidates are matched against), so bar 1 of a dense band leaves one
+    tracker parked on the last bin."""
+    n = 2048
+    sp = np.ones(n // 2)
+    t = oracle.Tracker()
+    idx, per = t.step(sp, n, 18.0, 52.0)                 # band = bins 40..113
+    assert len(t.trackers()) == 1 and t.trackers()[0][0] == 113
+    assert idx[0] == 113 and per[0] == n / 113 and np.all(idx[1:] == 0) and np.all(per[1:] == 0.0)
+
+
+def test_tracker_wide_bins_each_get_a_tracker_and_slots_fill_by_power(oracle):
+    n = 64
+    sp = np.zeros(n // 2); sp[4:9] = [1.0, 5.0, 3.0, 5.0, 2.0]        # periods 16, 12.8, 10.7, 9.1, 8 (>5 % apart)
+    t = oracle.Tracker()
+    idx, per = t.step(sp, n, 8.0, 16.0)
+    assert [x[0] for x in t.trackers()] == [4, 5, 6, 7, 8]
+    # descending power, equal powers keep bin order (stable bubble sort with '<')
+    assert list(idx[:5]) == [5, 7, 6, 8, 4] and np.all(idx[5:] == 0)
+    # slots are sticky: a new ordering of the powers does not move them
+    sp[4:9] = [9.0, 1.0, 1.0, 1.0, 1.0]
+    idx2, _ = t.step(sp, n, 8.0, 16.0)
+    assert list(idx2[:5]) == [5, 7, 6, 8, 4]
+
+
+def test_tracker_unseen_trackers_expire_and_slots_keep_raw_indices(oracle):
+    n = 64
+    sp = np.zeros(n // 2); sp[4:9] = [1.0, 5.0, 3.0, 4.0, 2.0]
+    t = oracle.Tracker()
+    t.step(sp, n, 8.0, 16.0)                              # trackers for bins 4..8
+    for _ in range(3):                                    # band shrinks: bins 4,5 are no longer candidates
+        idx, per = t.step(sp, n, 8.0, 10.7)               # band = bins 6..8
+    assert [x[0] for x in t.trackers()] == [6, 7, 8]      # bins 4, 5 erased after 3 inactive bars
+    # erase shifts the array but the slot table keeps raw indices (:1514-1519, :1584-1589):
+    # slot 0 pointed at tracker index 1 (bin 5) and now silently shows what slid into index 1
+    assert idx[0] == 7
+
+
 # ---- pipeline (bar loop) ------------------------------------------------------------------------
 def test_pipeline_series_matches_stagewise_calls(oracle):
     n = 256
