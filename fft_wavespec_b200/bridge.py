@@ -46,6 +46,12 @@ class PipelineCfg(C.Structure):
         ("tracker_tolerance", C.c_double), ("tracker_max_inactive", C.c_int32), ("reserved0", C.c_int32)]
 
 
+class CacheParams(C.Structure):
+    """wavespec_cache_params (include/wavespec_abi.h)."""
+    _fields_ = [("music_only", C.c_int32), ("use_music_weights", C.c_int32), ("min_coherence", C.c_double),
+                ("min_score", C.c_double), ("min_snr_db", C.c_double)]
+
+
 class WaveSpecError(RuntimeError):
     def __init__(self, status, text):
         super().__init__(f"{STATUS_NAMES.get(status, status)}: {text}")
@@ -94,6 +100,8 @@ def lib():
     L.wavespec_pla_windows_host.restype = i32
     L.wavespec_zigzag_feed_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, dbl, i32, vp, vp]
     L.wavespec_zigzag_feed_host.restype = i32
+    L.wavespec_cycle_cache_host.argtypes = [vp, i32, i32, i32, i32, i32, i32, dbl, C.POINTER(CacheParams), vp]
+    L.wavespec_cycle_cache_host.restype = i32
     L.wavespec_launch_count.argtypes = []; L.wavespec_launch_count.restype = i64
     L.wavespec_last_kernel.argtypes = []; L.wavespec_last_kernel.restype = C.c_char_p
     L.wavespec_version.argtypes = []; L.wavespec_version.restype = i32
@@ -107,7 +115,7 @@ EXPORTED_SYMBOLS = [
     "gpu_get_last_error_w", "gpu_fft_real_inverse", "gpu_fft_real_forward_batch",
     "wavespec_default_cfg", "wavespec_num_windows", "wavespec_pipeline_host", "wavespec_pipeline_device",
     "wavespec_fft_real_forward_sliding", "wavespec_pla_windows_host", "wavespec_zigzag_feed_host",
-    "wavespec_launch_count",
+    "wavespec_cycle_cache_host", "wavespec_launch_count",
     "wavespec_last_kernel", "wavespec_version",
 ]
 
@@ -284,6 +292,19 @@ def zigzag_feed_host(zz_main, zz_high, zz_low, window_len, hop=1, pivot_rule=0, 
     _check(lib().wavespec_zigzag_feed_host(_ptr(m), _ptr(h), _ptr(lo), m.size, window_len, hop, pivot_rule, mode,
                                            float(fallback), min_pivots, _ptr(lines), _ptr(valid)))
     return lines, valid
+
+
+def cycle_cache_host(rows, top_k, window_len, hop, bars, period_seconds=60.0, music_only=False,
+                     use_music_weights=False, min_coherence=0.05, min_score=0.01, min_snr_db=-40.0):
+    r = _f64(rows)
+    stride = r.shape[-1]
+    r2 = r.reshape(-1, stride)
+    n_windows = r2.shape[0] // top_k
+    cp = CacheParams(int(music_only), int(use_music_weights), min_coherence, min_score, min_snr_db)
+    out = np.empty((bars, 20))
+    _check(lib().wavespec_cycle_cache_host(_ptr(r2), n_windows, top_k, stride, window_len, hop, bars,
+                                           float(period_seconds), C.byref(cp), _ptr(out)))
+    return out
 
 
 def launch_count() -> int:

@@ -23,6 +23,7 @@ SOURCES = [
     ("ws_series.cu", ["-fmad=false"]),
     ("ws_pla.cu", ["-fmad=false"]),
     ("ws_zigzag.cu", ["-fmad=false"]),
+    ("ws_cache.cu", ["-fmad=false"]),
 ]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

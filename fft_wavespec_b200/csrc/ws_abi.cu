@@ -877,4 +877,26 @@ int32_t wavespec_zigzag_feed_host(const double* zz_main, const double* zz_high, 
     return WAVESPEC_OK;
 }
 
+int32_t wavespec_cycle_cache_host(const double* rows, int32_t n_windows, int32_t top_k, int32_t stride,
+                                  int32_t window_len, int32_t hop, int32_t bars, double period_seconds,
+                                  const wavespec_cache_params* params, double* out) {
+    int rc = ensure_open();
+    if (rc) return rc;
+    if (!rows || !out || !params) return fail(WAVESPEC_BAD_ARGS, "null buffer");
+    if (n_windows < 1 || top_k < 1 || stride < 14 || window_len < 1 || hop < 1 || bars < 1)
+        return fail(WAVESPEC_BAD_ARGS, "bad shape (stride must be >= 14)");
+    DeviceBuf dr, dout;
+    const size_t rb = (size_t)n_windows * top_k * stride * 8;
+    WS_CUDA(dr.alloc(rb), "cudaMalloc(rows)");
+    WS_CUDA(dout.alloc((size_t)bars * 20 * 8), "cudaMalloc(cache)");
+    cudaStream_t st = pick_stream();
+    WS_CUDA(cudaMemcpyAsync(dr.p, rows, rb, cudaMemcpyHostToDevice, st), "H2D rows");
+    WS_CUDA(ws::launch_cycle_cache(dr.as<double>(), n_windows, top_k, stride, window_len, hop, bars, period_seconds,
+                                   *params, dout.as<double>(), st), "cycle_cache kernel");
+    g_launches++;
+    WS_CUDA(cudaMemcpyAsync(out, dout.p, dout.bytes, cudaMemcpyDeviceToHost, st), "D2H cache");
+    WS_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    return WAVESPEC_OK;
+}
+
 }  // extern "C"

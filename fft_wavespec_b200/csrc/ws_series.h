@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/wavespec_abi.h"
 #include "ws_common.cuh"
 
 namespace ws {
@@ -60,6 +61,11 @@ cudaError_t launch_zigzag(const double* zmain, const double* zhigh, const double
                           int32_t n_series, int32_t len, int32_t N, int32_t hop, int rule, int mode, int min_pivots,
                           double* pv, int32_t* prev, int32_t* next, double* lines, int32_t* valid,
                           cudaStream_t stream);
+
+// ws_cache.cu
+cudaError_t launch_cycle_cache(const double* rows, int64_t n_windows, int32_t top_k, int32_t stride, int32_t N,
+                               int32_t hop, int64_t bars, double period_seconds, const ::wavespec_cache_params& cp,
+                               double* out, cudaStream_t stream);
 
 // ws_inverse.cu
 cudaError_t launch_inverse_real(const double* d_spec, int32_t N, int32_t n_windows, const double2* tw,

@@ -241,6 +241,26 @@ WAVESPEC_API int32_t wavespec_zigzag_feed_host(const double* zz_main, const doub
                                                int32_t mode, double fallback, int32_t min_pivots,
                                                double* lines, int32_t* valid);
 
+/* Batch result -> per-bar cycle cache record, on the device.  Replaces the
+ * indicator's O(rows x N) sine back-propagation loop (WaveSpecZZ_1.1.0-gpuopt.mq5:1067-1099) and
+ * yields exactly what SaveCycleCache writes (:294-324): 20 doubles per bar,
+ * [Wave1 Wave2 Period1 Period2 Eta1 Eta2 Phase1 Phase2 Energy1 Energy2 Coher1 Coher2 Snr1 Snr2
+ *  Score1 Score2 Eigen1 Eigen2 EtaConf1 EtaConf2], EMPTY_VALUE (DBL_MAX) where the loop writes nothing.
+ * `rows` is the buffer gpu_try_get_cycles_batch fills (n_windows * top_k rows of `stride` doubles,
+ * stride >= 14); `bars` is the series length (`got`).  The inputs of the weighting are the
+ * indicator's inputs (:71-77, :64). */
+typedef struct wavespec_cache_params {
+    int32_t music_only;          /* InpMusicOnly: rows with method != 1 are skipped              */
+    int32_t use_music_weights;   /* InpUseMusicWeights                                           */
+    double  min_coherence;       /* InpMinCoherence (0.05)                                       */
+    double  min_score;           /* InpMinScore (0.01)                                           */
+    double  min_snr_db;          /* InpMinSnrDb (-40)                                            */
+} wavespec_cache_params;
+WAVESPEC_API int32_t wavespec_cycle_cache_host(const double* rows, int32_t n_windows, int32_t top_k,
+                                               int32_t stride, int32_t window_len, int32_t hop,
+                                               int32_t bars, double period_seconds,
+                                               const wavespec_cache_params* params, double* out);
+
 /* Number of kernels launched by this library since gpu_init (bench.py `gpu_launches`). */
 WAVESPEC_API int64_t wavespec_launch_count(void);
 

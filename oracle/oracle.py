@@ -91,6 +91,8 @@ def lib():
     L.oracle_tracker_reset.argtypes = [C.POINTER(TrackerState)]
     L.oracle_tracker_step.argtypes = [C.POINTER(TrackerState), _dp, C.c_int, C.c_double, C.c_double, C.c_double,
                                       C.c_int, _ip, _dp]
+    L.oracle_cycle_cache.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                     C.c_int, C.c_double, C.c_double, C.c_double, _dp]
     L.oracle_default_cfg.argtypes = [C.POINTER(PipelineCfg), C.c_int]
     L.oracle_pipeline_series.argtypes = [_dp, C.c_int, C.POINTER(PipelineCfg)] + [C.c_void_p] * 7
     L.oracle_pipeline_series_trk.argtypes = [_dp, C.c_int, C.POINTER(PipelineCfg)] + [C.c_void_p] * 9
@@ -204,6 +206,16 @@ def zigzag_series_legacy(zz_main, zz_high, zz_low, mode):
     m = _f64(zz_main); out = np.zeros_like(m)
     ok = lib().oracle_zigzag_series_legacy(m, _f64(zz_high), _f64(zz_low), m.size, int(mode), out)
     return bool(ok), out
+
+
+def cycle_cache(rows, top_k, window_len, hop, bars, period_seconds=60.0, music_only=False, use_music_weights=False,
+                min_coherence=0.05, min_score=0.01, min_snr_db=-40.0):
+    """rows: [n_windows*top_k, stride] -> [bars, 20] cache record (EMPTY_VALUE = DBL_MAX where unwritten)."""
+    r = _f64(rows).reshape(-1, np.asarray(rows).shape[-1])
+    out = np.empty((bars, 20))
+    lib().oracle_cycle_cache(r, r.shape[0], r.shape[1], top_k, window_len, hop, bars, period_seconds,
+                             int(music_only), int(use_music_weights), min_coherence, min_score, min_snr_db, out)
+    return out
 
 
 class Tracker:

@@ -6,6 +6,7 @@
 // -ffp-contract=off), MathRound = round half away from zero, (int) truncates.
 #include "wavespec_oracle.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstring>
@@ -547,6 +548,49 @@ int oracle_zigzag_series_legacy(const double* zz_main, const double* zz_high, co
     double last_val = pval[pc - 1];
     for (int j = last_idx; j < n; ++j) price_data[j] = last_val;
     return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A8c R/WaveSpecZZ_1.1.0-gpuopt.mq5:1044-1099 + record layout of SaveCycleCache :294-324
+void oracle_cycle_cache(const double* cycles, int out_len, int stride, int top_k, int window_len, int hop,
+                        int got, double period_seconds, int music_only, int use_music_weights,
+                        double min_coherence, double min_score, double min_snr_db, double* out) {
+    const double EMPTY = 1.7976931348623157e308;   // EMPTY_VALUE
+    // buffer b of slot-pair p lives at out[idx*20 + 2*b + p]  (Wave, Period, Eta, Phase, Energy, Coher, Snr, Score, Eigen, EtaConf)
+    for (int64_t i = 0; i < (int64_t)got * 20; i++) out[i] = EMPTY;
+    const double two_pi = 6.28318530717958647692;
+    for (int c = 0; c < out_len; ++c) {
+        const int64_t base = (int64_t)c * stride;
+        int method_id = (stride > 14 ? (int)cycles[base + 14] : 0);
+        if (music_only && method_id != 1) continue;
+        double amp = cycles[base + 0], freq = cycles[base + 1], period = cycles[base + 2], phase = cycles[base + 3];
+        double eta_sec = cycles[base + 5];
+        double energy = cycles[base + 6], coher = cycles[base + 7], snr = cycles[base + 8], eigen = cycles[base + 10],
+               score = cycles[base + 11], etac = cycles[base + 13];
+        double w_energy = std::fmax(energy, 0.0);
+        double w_coher = std::fmax(coher, 0.0);
+        double w_score = std::fmax(score, 0.0);
+        double snr_eff = std::fmax(snr, min_snr_db);
+        double w_snr = 1.0 / (1.0 + std::pow(10.0, -snr_eff / 10.0));
+        double weight_total = use_music_weights ? (w_energy * w_coher * w_score * w_snr) : 1.0;
+        if (coher < min_coherence || score < min_score) weight_total = 0.0;
+        int window_idx = c / top_k;
+        int start_bar = window_idx * hop;
+        if (start_bar >= got) continue;
+        double omega = two_pi * freq;
+        int recon_span = std::min(window_len - 1, got - start_bar - 1);
+        int slot = c % top_k;
+        const int p = (slot == 0) ? 0 : 1;
+        for (int k = 0; k <= recon_span; ++k) {
+            int idx = start_bar + k;
+            double theta = phase - omega * k;
+            double val = amp * weight_total * std::sin(theta);
+            double* o = out + (int64_t)idx * 20;
+            o[0 + p] = val; o[2 + p] = period; o[4 + p] = std::fmax(eta_sec - k * period_seconds, 0.0);
+            o[6 + p] = theta; o[8 + p] = energy; o[10 + p] = coher; o[12 + p] = snr; o[14 + p] = score;
+            o[16 + p] = eigen; o[18 + p] = etac;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -122,6 +122,13 @@ void oracle_tracker_step(oracle_tracker_state* st, const double* spectrum, int n
                          double max_period, double tolerance_pct, int max_inactive_bars,
                          int32_t* slot_index, double* slot_period);
 
+/* A8c + cache record: R/WaveSpecZZ_1.1.0-gpuopt.mq5:1044-1099 (buffers initialised to EMPTY_VALUE,
+ * sine back-propagation of every row over up to N bars, later rows overwrite) followed by the
+ * 20-doubles-per-bar record of SaveCycleCache (:294-324).  out has bars * 20 doubles. */
+void oracle_cycle_cache(const double* rows, int out_len, int stride, int top_k, int window_len, int hop,
+                        int bars, double period_seconds, int music_only, int use_music_weights,
+                        double min_coherence, double min_score, double min_snr_db, double* out);
+
 /* ---- per-series pipelines (bar loops), used by parity tests and the timed CPU baseline ---- */
 typedef struct oracle_pipeline_cfg {
     int window_len, hop, top_k, row_stride;

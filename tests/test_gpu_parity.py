@@ -558,3 +558,49 @@ def test_tracker_pool_slots_match_oracle(br, oracle, case):
             assert np.array_equal(got["bins"][i], ref["bins"])
         if "rows" in ref:
             assert np.abs(got["rows"][i][..., 0] - ref["rows"][..., 0]).max() <= REL_TOL * ref["rows"][..., 0].max()
+
+
+# ---- 8f rank 2: device-side decode of the batch result into the cycle-cache record --------------
+@pytest.mark.parametrize("hop,top_k,music_only,weights", [(1, 4, False, False), (1, 2, False, True),
+                                                           (3, 4, False, True), (1, 1, False, False),
+                                                           (1, 4, True, True), (7, 3, True, False)])
+def test_cycle_cache_record_matches_sequential_decode(br, oracle, hop, top_k, music_only, weights):
+    N, bars = 128, 700
+    rng = np.random.default_rng(hop * 10 + top_k)
+    nwin = 1 + (bars - N) // hop
+    rows = np.zeros((nwin * top_k, 15))
+    rows[:, 0] = rng.random(rows.shape[0]) * 1e-3            # amplitude
+    rows[:, 1] = rng.random(rows.shape[0]) * 0.2 + 0.005     # freq
+    rows[:, 2] = 1.0 / rows[:, 1]
+    rows[:, 3] = rng.uniform(-np.pi, np.pi, rows.shape[0])
+    rows[:, 5] = rng.random(rows.shape[0]) * 3000
+    rows[:, 6:14] = rng.random((rows.shape[0], 8))
+    rows[:, 8] = rng.uniform(-60, 30, rows.shape[0])         # snr_db
+    rows[:, 14] = (rng.random(rows.shape[0]) < 0.7).astype(float)   # mixed methods: exercises the skip search
+    kw = dict(period_seconds=60.0, music_only=music_only, use_music_weights=weights)
+    got = br.cycle_cache_host(rows, top_k, N, hop, bars, **kw)
+    ref = oracle.cycle_cache(rows, top_k, N, hop, bars, **kw)
+    empty = ref == np.finfo(float).max
+    assert np.array_equal(got == np.finfo(float).max, empty)
+    den = np.maximum(1e-300, np.abs(ref[~empty]))
+    assert (np.abs(got[~empty] - ref[~empty]) / den).max() < 1e-9 or np.abs(got[~empty] - ref[~empty]).max() < 1e-15
+
+
+def test_cycle_cache_from_library_rows(br, oracle):
+    """End to end: batch API rows -> cache record; FFT-ridge rows carry method 0, so with
+    InpMusicOnly the record is all EMPTY_VALUE, and with it off buffer 1 holds amp*sin(phase)."""
+    s = synth.random_walk(950, 1500)
+    cfg = br.default_cfg(256, top_k=4, min_period=9.0, max_period=100.0)
+    rows = br.pipeline_host(s, cfg, br.OUT_ROWS)["rows"]
+    rec = br.cycle_cache_host(rows, 4, 256, 1, 1500, music_only=True)
+    assert np.all(rec == np.finfo(float).max)
+    # the MUSIC quality fields of FFT-ridge rows are 0, and the decode zero-weights rows below
+    # InpMinCoherence / InpMinScore (:1079) even with InpUseMusicWeights off: both go to 0
+    kw = dict(music_only=False, use_music_weights=False, min_coherence=0.0, min_score=0.0)
+    zero = br.cycle_cache_host(rows, 4, 256, 1, 1500, music_only=False, use_music_weights=False)
+    assert np.all(zero[:, 0] == 0.0)
+    rec = br.cycle_cache_host(rows, 4, 256, 1, 1500, **kw)
+    ref = oracle.cycle_cache(rows, 4, 256, 1, 1500, **kw)
+    nw = rows.shape[0]
+    assert np.abs(rec[:nw, 0] - rows[:, 0, 0] * np.sin(rows[:, 0, 3])).max() < 1e-15   # k = 0 for every bar < nwin
+    assert np.abs(rec - ref).max() / 1.0 < 1e-9 or np.array_equal(rec, ref)
