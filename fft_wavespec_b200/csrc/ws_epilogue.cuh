@@ -142,31 +142,52 @@ __device__ __forceinline__ void warp_select_emit(const Params& p, double* pw, co
 // lo    : first bin of the band;  nvalid : windows of the batch that exist (<= wpb)
 // gw0   : global window index of the batch's first window (series * nwin + window)
 // stage : shared, per-warp scratch of 32 * 16 doubles (used when row_stride <= 16)
+// LG: compile-time group width (8: the common case K <= 8, band <= 64 — scans and shuffle ladders
+// fully unrolled, no loop or address arithmetic left); 0: run-time width Lg_rt.
+template <int LG>
 __device__ __forceinline__ void warp_select_emit_batch(const Params& p, double* pw, const double2* xb,
-                                                       int band, int lo, int Lg, int nvalid, int64_t gw0,
+                                                       int band, int lo, int Lg_rt, int nvalid, int64_t gw0,
                                                        double* stage) {
+    // LG == 8: pw rows are padded to 64 entries, out-of-band and non-existing windows hold -2, so
+    // the scans load unconditionally
     const int lane = threadIdx.x & 31;
+    const int Lg = LG ? LG : Lg_rt;
     const int g = lane / Lg, l = lane - g * Lg;
     const int N = p.N, K = p.K;
-    double* pwb = pw + g * band;
+    double* pwb = pw + g * (LG == 8 ? 64 : band);
     const double2* xbb = xb + g * band;
     const bool live = g < nvalid;
 
     double bsum = 0.0;
-    if (live) for (int e = l; e < band; e += Lg) bsum += pwb[e];
-    for (int m = Lg >> 1; m >= 1; m >>= 1) bsum += shfl_xor_d(bsum, m);
+    if (LG == 8) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const double v = pwb[l + 8 * i]; bsum += (v >= 0.0) ? v : 0.0; }
+#pragma unroll
+        for (int m = 4; m >= 1; m >>= 1) bsum += shfl_xor_d(bsum, m);
+    } else {
+        if (live) for (int e = l; e < band; e += Lg) bsum += pwb[e];
+        for (int m = Lg >> 1; m >= 1; m >>= 1) bsum += shfl_xor_d(bsum, m);
+    }
 
     int my_pos = -1;
     double my_pow = -1.0;
     for (int r = 0; r < K; r++) {
         double bp = -1.0; int bpos = 0x7fffffff;
-        if (live)
+        // ascending scan inside a lane: an equal power met later never displaces the earlier
+        // (lower) bin, so strict '>' alone implements the tie rule here
+        if (LG == 8) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int e = l + 8 * i;
+                const double v = pwb[e];
+                if (v > bp) { bp = v; bpos = e; }
+            }
+        } else if (live) {
             for (int e = l; e < band; e += Lg) {
-                // ascending scan inside a lane: an equal power met later never displaces the earlier
-                // (lower) bin, so strict '>' alone implements the tie rule here
                 double v = pwb[e];
                 if (v > bp) { bp = v; bpos = e; }
             }
+        }
         {
             // Cross-lane argmax of (power desc, position asc) inside the group.  Fast path: the
             // high word of a non-negative double orders like the double; when exactly one lane
@@ -174,7 +195,12 @@ __device__ __forceinline__ void warp_select_emit_batch(const Params& p, double* 
             // broadcast.  Otherwise (ties in the top 32 bits) fall back to the full comparison.
             const int hi = (bp >= 0.0) ? __double2hiint(bp) + 1 : 0;      // 0 = no candidate
             int mh = hi;
-            for (int m = Lg >> 1; m >= 1; m >>= 1) mh = max(mh, __shfl_xor_sync(0xffffffffu, mh, m));
+            if (LG == 8) {
+#pragma unroll
+                for (int m = 4; m >= 1; m >>= 1) mh = max(mh, __shfl_xor_sync(0xffffffffu, mh, m));
+            } else {
+                for (int m = Lg >> 1; m >= 1; m >>= 1) mh = max(mh, __shfl_xor_sync(0xffffffffu, mh, m));
+            }
             const unsigned cand = __ballot_sync(0xffffffffu, hi == mh && mh != 0);
             const unsigned gmask = (Lg == 32 ? 0xffffffffu : ((1u << Lg) - 1u)) << (g * Lg);
             const unsigned mine = cand & gmask;

@@ -154,13 +154,26 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     if (lay.cta_epi == 2) {
         // insertion rule, several windows per warp (ws_epilogue.cuh)
         double* pwa = reinterpret_cast<double*>(ov);
-        for (int i = tid; i < nvalid * band; i += kSlideThreads) { double2 v = top.xb[i]; pwa[i] = v.x * v.x + v.y * v.y; }
+        const int pws = lay.Lg == 8 ? 64 : band;          // padded rows for the unrolled epilogue
+        if (lay.Lg == 8) {
+            for (int i = tid; i < pl.T * 64; i += kSlideThreads) {
+                const int wl = i >> 6, e = i & 63;
+                double v = -2.0;
+                if (wl < nvalid && e < band) { const double2 x = top.xb[wl * band + e]; v = x.x * x.x + x.y * x.y; }
+                pwa[i] = v;
+            }
+        } else {
+            for (int i = tid; i < nvalid * band; i += kSlideThreads) { double2 v = top.xb[i]; pwa[i] = v.x * v.x + v.y * v.y; }
+        }
         __syncthreads();
         const int wpb = 32 / lay.Lg;
-        double* stage = reinterpret_cast<double*>(ov + ((pl.T * band * 8 + 15) & ~15)) + warp * 512;
+        double* stage = reinterpret_cast<double*>(ov + ((pl.T * pws * 8 + 15) & ~15)) + warp * 512;
         for (int b0 = warp * wpb; b0 < nvalid; b0 += (kSlideThreads / 32) * wpb) {
             const int nb = (nvalid - b0) < wpb ? (nvalid - b0) : wpb;
-            warp_select_emit_batch(p, pwa + b0 * band, top.xb + b0 * band, band, lo, lay.Lg, nb, gw_tile + b0, stage);
+            if (lay.Lg == 8)
+                warp_select_emit_batch<8>(p, pwa + b0 * 64, top.xb + b0 * band, band, lo, 8, nb, gw_tile + b0, stage);
+            else
+                warp_select_emit_batch<0>(p, pwa + b0 * band, top.xb + b0 * band, band, lo, lay.Lg, nb, gw_tile + b0, stage);
         }
         return;
     }
@@ -217,7 +230,7 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
     }
     int ov_bytes;
     if (lay.cta_epi == 2) {
-        ov_bytes = ((pl.T * lay.band * 8 + 15) & ~15) + warps * 512 * 8;
+        ov_bytes = ((pl.T * (lay.Lg == 8 ? 64 : lay.band) * 8 + 15) & ~15) + warps * 512 * 8;
     } else {
         ov_bytes = pl.T * lay.band * 8 + warps * lay.band * 4;
     }
