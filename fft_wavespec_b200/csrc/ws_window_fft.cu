@@ -7,8 +7,8 @@
 //
 // One CTA owns a tile of consecutive windows of one series.  The tile's samples are staged in
 // shared memory once (each sample is read from HBM once per tile, not once per window).  Each
-// window becomes an N/2-point complex Stockham FFT (radix-4 passes + one radix-2 pass when
-// log2(N/2) is odd) of z[m] = v[2m] + i v[2m+1] held in shared memory, followed by the
+// window becomes an N/2-point complex Stockham FFT (radix-8 passes in registers + one radix-4 or
+// radix-2 pass for the remaining bits) of z[m] = v[2m] + i v[2m+1] exchanged through shared memory, followed by the
 // real-input split, the power spectrum and a warp-per-window top-K epilogue.
 //
 // The transform uses exact table twiddles, not the reference's multiplicative recurrence
@@ -41,6 +41,60 @@ __device__ __forceinline__ void r4_butterfly(double2& a0, double2& a1, double2& 
     double2 d = csub(a1, a3);
     double2 b3 = make_double2(d.y, -d.x);   // -i * (a1 - a3)
     a0 = cadd(b0, b2); a2 = csub(b0, b2); a1 = cadd(b1, b3); a3 = csub(b1, b3);
+}
+
+// forward 8-point DFT in registers (decimation in frequency; outputs in natural order)
+__device__ __forceinline__ void r8_butterfly(double2* a) {
+    const double h = 0.70710678118654752440;
+    double2 b0 = cadd(a[0], a[4]), b1 = cadd(a[1], a[5]), b2 = cadd(a[2], a[6]), b3 = cadd(a[3], a[7]);
+    double2 d0 = csub(a[0], a[4]), t1 = csub(a[1], a[5]), t2 = csub(a[2], a[6]), t3 = csub(a[3], a[7]);
+    double2 d1 = make_double2((t1.x + t1.y) * h, (t1.y - t1.x) * h);        // * W8
+    double2 d2 = make_double2(t2.y, -t2.x);                                   // * -i
+    double2 d3 = make_double2((t3.y - t3.x) * h, -(t3.x + t3.y) * h);       // * W8^3
+    double2 c0 = cadd(b0, b2), c1 = cadd(b1, b3), c2 = csub(b0, b2), u = csub(b1, b3);
+    double2 c3 = make_double2(u.y, -u.x);
+    double2 e0 = cadd(d0, d2), e1 = cadd(d1, d3), e2 = csub(d0, d2), v = csub(d1, d3);
+    double2 e3 = make_double2(v.y, -v.x);
+    a[0] = cadd(c0, c1); a[4] = csub(c0, c1); a[2] = cadd(c2, c3); a[6] = csub(c2, c3);
+    a[1] = cadd(e0, e1); a[5] = csub(e0, e1); a[3] = cadd(e2, e3); a[7] = csub(e2, e3);
+}
+
+// One Stockham pass of radix R over nw windows of M points: thread item j reads in[j + r M/R],
+// multiplies by W^{r k} (k = j mod Ns), does the R-point DFT and writes out[(j-k) R + k + r Ns].
+// LOAD(wl, m) supplies element m of window wl (the first pass reads the staged samples through
+// the prologue, the others the previous pass's buffer).
+template <int R, int kThreads, class Load>
+__device__ __forceinline__ void stockham_pass(Load load, double2* out, int nw, int M, int N, int Ns,
+                                              const double2* __restrict__ tw) {
+    const int q = M / R;
+    const int tstep = N / (R * Ns);
+    for (int idx = threadIdx.x; idx < nw * q; idx += kThreads) {
+        const int wl = idx / q, j = idx - wl * q;
+        const int k = j & (Ns - 1);
+        double2 a[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) a[r] = load(wl, j + r * q);
+        if (Ns > 1) {
+            const int t = tstep * k;
+            if (R == 8) {
+                // three table loads; the other four twiddles are products (FP64 is idle here, the
+                // loads are what stalls: ncu long-scoreboard)
+                const double2 w1 = __ldg(tw + t), w2 = __ldg(tw + 2 * t), w4 = __ldg(tw + 4 * t);
+                const double2 w3 = cmul(w1, w2), w5 = cmul(w1, w4), w6 = cmul(w2, w4), w7 = cmul(w3, w4);
+                a[1] = cmul(a[1], w1); a[2] = cmul(a[2], w2); a[3] = cmul(a[3], w3); a[4] = cmul(a[4], w4);
+                a[5] = cmul(a[5], w5); a[6] = cmul(a[6], w6); a[7] = cmul(a[7], w7);
+            } else {
+#pragma unroll
+                for (int r = 1; r < R; r++) a[r] = cmul(a[r], __ldg(tw + r * t));
+            }
+        }
+        if (R == 8) r8_butterfly(a);
+        else if (R == 4) r4_butterfly(a[0], a[1], a[2], a[3]);
+        else { double2 x0 = a[0], x1 = a[1]; a[0] = cadd(x0, x1); a[1] = csub(x0, x1); }
+        double2* o = out + (size_t)wl * M + (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; r++) o[r * Ns] = a[r];
+    }
 }
 
 // Trend IIR of Legacy/...-kalman-fast.mq5:3367-3379 over x[0..L): y[0] = c (x0 + x0),
@@ -91,10 +145,10 @@ window_fft_kernel(const Params p) {
     if (tw_count <= 0) return;
     const int Lt = (tw_count - 1) * p.hop + N;
 
-    // windows processed concurrently by the CTA: as many as keep every thread on one radix-4
-    // butterfly per pass (M/4 butterflies per window)
-    const int q = M >> 2;                          // butterflies per window per radix-4 pass
-    int wpc = q > 0 ? kThreads / q : kThreads;     // N >= 8
+    // windows processed concurrently by the CTA: as many as keep every thread on one radix-8
+    // butterfly per pass (M/8 butterflies per window), at most 4
+    const int q = M >> 3;                          // butterflies per window per radix-8 pass
+    int wpc = q > 0 ? kThreads / q : kThreads;
     if (wpc < 1) wpc = 1;
     if (wpc > 4) wpc = 4;
 
@@ -134,8 +188,6 @@ window_fft_kernel(const Params p) {
         }
     }
 
-    const int log2M = p.log2N - 1;
-    const bool odd = (log2M & 1) != 0;
 
     for (int wb = 0; wb < tw_count; wb += wpc) {
         const int nw = (tw_count - wb) < wpc ? (tw_count - wb) : wpc;
@@ -171,71 +223,41 @@ window_fft_kernel(const Params p) {
             __syncthreads();
         }
 
-        // ---- pass 0 (Ns = 1): straight from the staged samples through the prologue
+        // ---- mixed-radix Stockham passes: radix 8 while three bits remain, then one radix 4 / 2
         double2* in = bufA;
         double2* out = bufB;
-        if (M >= 4) {
-            for (int idx = tid; idx < nw * q; idx += kThreads) {
-                int wl = idx / q, j = idx - wl * q;
-                int off = from_feed ? wl * N : (wb + wl) * p.hop;
+        {
+            auto from_tile = [&](int wl, int m) {
+                const int off = from_feed ? wl * N : (wb + wl) * p.hop;
                 Prologue pr{tile, p.has_window ? p.wtab : nullptr, p.apow,
                             pro_mode ? delta[wb + wl] : 0.0, pro_mode};
-                double2 a[4];
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    int m = j + r * q;
-                    a[r] = make_double2(pr(off, 2 * m), pr(off, 2 * m + 1));
+                return make_double2(pr(off, 2 * m), pr(off, 2 * m + 1));
+            };
+            int rem = p.log2N - 1;                   // log2 M
+            int Ns = 1;
+            bool first = true;
+            if (rem == 0) {                          // M = 1 (N = 2): nothing to transform
+                for (int wl = tid; wl < nw; wl += kThreads) out[wl] = from_tile(wl, 0);
+                __syncthreads();
+                double2* t = in; in = out; out = t;
+            }
+            while (rem > 0) {
+                const int lr = rem >= 3 ? 3 : rem;
+                const double2* src = in;
+                auto from_buf = [&](int wl, int m) { return src[(size_t)wl * M + m]; };
+                if (first) {
+                    if (lr == 3) stockham_pass<8, kThreads>(from_tile, out, nw, M, N, Ns, p.tw);
+                    else if (lr == 2) stockham_pass<4, kThreads>(from_tile, out, nw, M, N, Ns, p.tw);
+                    else stockham_pass<2, kThreads>(from_tile, out, nw, M, N, Ns, p.tw);
+                } else {
+                    if (lr == 3) stockham_pass<8, kThreads>(from_buf, out, nw, M, N, Ns, p.tw);
+                    else if (lr == 2) stockham_pass<4, kThreads>(from_buf, out, nw, M, N, Ns, p.tw);
+                    else stockham_pass<2, kThreads>(from_buf, out, nw, M, N, Ns, p.tw);
                 }
-                r4_butterfly(a[0], a[1], a[2], a[3]);
-                double2* o = out + (size_t)wl * M + 4 * j;
-                o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = a[3];
+                __syncthreads();
+                double2* t = in; in = out; out = t;
+                Ns <<= lr; rem -= lr; first = false;
             }
-        } else {
-            // M = 1 or 2 (N = 2, 4): copy through the prologue; the radix-2 tail finishes it
-            for (int idx = tid; idx < nw * M; idx += kThreads) {
-                int wl = idx / M, m = idx - wl * M;
-                int off = from_feed ? wl * N : (wb + wl) * p.hop;
-                Prologue pr{tile, p.has_window ? p.wtab : nullptr, p.apow,
-                            pro_mode ? delta[wb + wl] : 0.0, pro_mode};
-                out[(size_t)wl * M + m] = make_double2(pr(off, 2 * m), pr(off, 2 * m + 1));
-            }
-        }
-        __syncthreads();
-        { double2* t = in; in = out; out = t; }
-
-        // ---- remaining radix-4 passes
-        int Ns = (M >= 4) ? 4 : 1;
-        for (; Ns * 4 <= M; Ns <<= 2) {
-            const int tstep = N / (4 * Ns);
-            for (int idx = tid; idx < nw * q; idx += kThreads) {
-                int wl = idx / q, j = idx - wl * q;
-                const double2* iw = in + (size_t)wl * M;
-                int k = j & (Ns - 1);
-                double2 a0 = iw[j], a1 = iw[j + q], a2 = iw[j + 2 * q], a3 = iw[j + 3 * q];
-                int t = tstep * k;
-                a1 = cmul(a1, __ldg(p.tw + t));
-                a2 = cmul(a2, __ldg(p.tw + 2 * t));
-                a3 = cmul(a3, __ldg(p.tw + 3 * t));
-                r4_butterfly(a0, a1, a2, a3);
-                double2* o = out + (size_t)wl * M + ((j - k) << 2) + k;
-                o[0] = a0; o[Ns] = a1; o[2 * Ns] = a2; o[3 * Ns] = a3;
-            }
-            __syncthreads();
-            double2* t = in; in = out; out = t;
-        }
-        // ---- radix-2 tail when log2(M) is odd (or M == 2)
-        if ((odd && M >= 2) || M == 2) {
-            const int h = M >> 1;
-            for (int idx = tid; idx < nw * h; idx += kThreads) {
-                int wl = idx / h, j = idx - wl * h;
-                const double2* iw = in + (size_t)wl * M;
-                double2 a0 = iw[j];
-                double2 a1 = cmul(iw[j + h], __ldg(p.tw + 2 * j));
-                double2* o = out + (size_t)wl * M;
-                o[j] = cadd(a0, a1); o[j + h] = csub(a0, a1);
-            }
-            __syncthreads();
-            double2* t = in; in = out; out = t;
         }
 
         // ---- real-input split: X[k] = E + W_N^k O ; power ; spectra store
@@ -323,7 +345,7 @@ window_fft_kernel(const Params p) {
 // Host-side launcher.  Returns the dynamic shared memory it used (0 on error).
 size_t window_fft_smem_bytes(const Params& p, int tile_windows, int kThreads) {
     const int N = p.N, M = N / 2;
-    int q = M / 4;
+    int q = M / 8;
     int wpc = q > 0 ? kThreads / q : kThreads;
     if (wpc < 1) wpc = 1;
     if (wpc > 4) wpc = 4;
@@ -339,12 +361,12 @@ int window_fft_pick_tile(const Params& p, int kThreads) {
     // tile sized so that the staged samples stay near 16 KB and, for the IIR detrend, fit the
     // scratch carved out of bufA (Lt <= 2*wpc*M doubles)
     const int N = p.N, M = N / 2;
-    int q = M / 4;
+    int q = M / 8;
     int wpc = q > 0 ? kThreads / q : kThreads;
     if (wpc < 1) wpc = 1;
     if (wpc > 4) wpc = 4;
     if (p.feed) return wpc;
-    long budget = 4096 > N + 63 ? 4096 : N + 63;  // doubles
+    long budget = N <= 1024 ? 4096 : N + 63;      // doubles (large N: keep shared memory for a third CTA)
     if (N >= 8192) budget = N;                    // shared memory is full: one window per tile
     long t = (budget - N) / p.hop + 1;
     if (t < 1) t = 1;
