@@ -424,25 +424,73 @@ int run_pipeline(const double* d_series, int32_t n_series, int32_t series_len,
     return WAVESPEC_OK;
 }
 
+// A13 host logic.  Which tracker a band bin matches, when trackers are appended, expire and shift
+// (Legacy/...-kalman-fast.mq5:1418-1529) depends on PERIODS only — never on the data — and every bar
+// presents the same bins in the same order.  So the tracker structure is one deterministic
+// sequence shared by all series, and it settles: from some bar B0 on it repeats itself, after
+// which the 12 slots (sticky, refilled only from unused trackers) cannot change any more.  This
+// returns B0 (first bar whose end state equals the previous bar's), or -1 if no fixed point shows
+// up within `limit` bars (then the device walks every bar).
+int64_t tracker_fixed_point(int N, int lo, int hi, double tol, int max_inactive, int64_t limit) {
+    struct T { double period; int idx; int inactive; bool active; };
+    std::vector<T> tr, prev;
+    auto same = [](double p1, double p2, double tolp) {
+        if (p1 <= 0 || p2 <= 0) return false;
+        double diff = std::fabs(p1 - p2), avg = (p1 + p2) / 2.0;
+        return (diff / avg) * 100.0 <= tolp;
+    };
+    for (int64_t b = 0; b < limit; b++) {
+        for (int j = lo; j <= hi; j++) {
+            double period = j > 0 ? (double)N / j : 0;
+            if (period <= 0) continue;
+            int best = -1; double smallest = 999999;
+            for (size_t i = 0; i < tr.size(); i++) {
+                if (tr[i].inactive > 0) continue;
+                double diff = std::fabs(tr[i].period - period);
+                if (same(period, tr[i].period, tol) && diff < smallest) { smallest = diff; best = (int)i; }
+            }
+            if (best >= 0) { tr[best].period = period; tr[best].idx = j; tr[best].active = true; tr[best].inactive = 0; }
+            else if ((int)tr.size() < ws::kTrackerCap) tr.push_back(T{period, j, 0, true});
+        }
+        for (int i = (int)tr.size() - 1; i >= 0; i--)
+            if (!tr[i].active && ++tr[i].inactive >= max_inactive) tr.erase(tr.begin() + i);
+        for (auto& t : tr) t.active = false;
+        bool eq = prev.size() == tr.size();
+        for (size_t i = 0; eq && i < tr.size(); i++)
+            eq = prev[i].period == tr[i].period && prev[i].idx == tr[i].idx && prev[i].inactive == tr[i].inactive;
+        if (eq && b > 0) return b;
+        prev = tr;
+    }
+    return -1;
+}
+
 // A13: FFT kernel -> compact band hand-off -> tracker kernel, chunked over windows so that the
-// hand-off buffer stays bounded; the tracker state of every series persists across chunks.
+// hand-off buffer stays bounded; the tracker state of every series persists across chunks.  The
+// sequential kernel only walks the bars up to the structural fixed point; the rest is a broadcast.
 int run_tracker_path(Params p, const wavespec_pipeline_cfg* c, int32_t* d_trk_index, double* d_trk_period,
                      bool plain, cudaStream_t st) {
     const int band = p.band_hi - p.band_lo + 1;
     const int64_t nwin = p.nwin;
+    const bool sel = p.rows || p.bins || p.waves || p.contrib;
+    const bool other = sel || p.spectra || p.phase;
+    static const bool walk_all = getenv("WAVESPEC_TRACKER_WALK_ALL") != nullptr;      // testing hook
+    int64_t fixed = walk_all ? -1 : tracker_fixed_point(p.N, p.band_lo, p.band_hi, c->tracker_tolerance,
+                                                        c->tracker_max_inactive, 4096);
+    // bars the sequential kernel has to walk: one past the fixed point (its slots are final)
+    const int64_t walk = (fixed < 0 || fixed + 1 >= nwin) ? nwin : fixed + 1;
+    const int64_t need = other ? nwin : walk;                 // windows the FFT kernels must cover
     const size_t per_win = (size_t)band * 16 * (size_t)p.n_series;
     int64_t wchunk = (int64_t)(((size_t)2 << 30) / per_win);
     if (wchunk < 1) wchunk = 1;
-    if (wchunk > nwin) wchunk = nwin;
+    if (wchunk > need) wchunk = need;
     DeviceBuf scratch, states;
     WS_CUDA(scratch.alloc(per_win * (size_t)wchunk), "cudaMalloc(band buffer)");
     WS_CUDA(states.alloc(sizeof(ws::TrackerState) * (size_t)p.n_series), "cudaMalloc(tracker state)");
-    const bool sel = p.rows || p.bins || p.waves || p.contrib;
     // the sliding kernel hands the band over only in its split form (insertion rule, K <= 8)
     bool use_sliding = plain && ws::sliding_shared_supported(p) && (!sel || ws::rows_from_band_supported(p));
-    for (int64_t wa = 0; wa < nwin; wa += wchunk) {
+    for (int64_t wa = 0; wa < need; wa += wchunk) {
         Params q = p;
-        q.win_offset = wa; q.chunk_nwin = (wa + wchunk <= nwin) ? wchunk : nwin - wa;
+        q.win_offset = wa; q.chunk_nwin = (wa + wchunk <= need) ? wchunk : need - wa;
         q.band_buf = scratch.as<double2>();
         if (use_sliding) {
             WS_CUDA(ws::launch_sliding_shared(q, st), "sliding_shared kernel");
@@ -454,9 +502,16 @@ int run_tracker_path(Params p, const wavespec_pipeline_cfg* c, int32_t* d_trk_in
             g_launches++;
             g_last_kernel = "window_fft";
         }
-        WS_CUDA(ws::launch_tracker(q.band_buf, p.band_lo, band, p.n_series, q.chunk_nwin, wa, nwin, p.N,
-                                   c->tracker_tolerance, c->tracker_max_inactive, states.as<ws::TrackerState>(),
-                                   d_trk_index, d_trk_period, st), "tracker kernel");
+        if (wa < walk) {
+            const int64_t np = (wa + q.chunk_nwin <= walk) ? q.chunk_nwin : walk - wa;
+            WS_CUDA(ws::launch_tracker(q.band_buf, p.band_lo, band, p.n_series, q.chunk_nwin, np, wa, nwin, p.N,
+                                       c->tracker_tolerance, c->tracker_max_inactive,
+                                       states.as<ws::TrackerState>(), d_trk_index, d_trk_period, st), "tracker kernel");
+            g_launches++;
+        }
+    }
+    if (walk < nwin) {
+        WS_CUDA(ws::launch_tracker_fill(p.n_series, nwin, walk - 1, d_trk_index, d_trk_period, st), "tracker fill kernel");
         g_launches++;
     }
     WS_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize(tracker)");      // scratch dies here

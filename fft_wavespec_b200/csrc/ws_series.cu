@@ -197,15 +197,16 @@ __global__ void wkalman_kernel(const double* __restrict__ contrib, const int32_t
 // The reference quirks are kept: inactive trackers are never re-matched (:1437), erasing shifts
 // the array while the slot table keeps raw indices (:1514-1519, :1584-1589).
 __global__ void tracker_kernel(const double2* __restrict__ band, int32_t band_lo, int32_t nband,
-                               int32_t n_series, int64_t chunk_nwin, int64_t win_offset, int64_t nwin, int32_t N,
-                               double tol, int32_t max_inactive, TrackerState* __restrict__ states,
-                               int32_t* __restrict__ trk_index, double* __restrict__ trk_period) {
+                               int32_t n_series, int64_t chunk_nwin, int64_t n_process, int64_t win_offset,
+                               int64_t nwin, int32_t N, double tol, int32_t max_inactive,
+                               TrackerState* __restrict__ states, int32_t* __restrict__ trk_index,
+                               double* __restrict__ trk_period) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_series) return;
     TrackerState& st = states[s];
     if (win_offset == 0) { st.count = 0; for (int i = 0; i < 12; i++) st.slot[i] = -1; }
     int count = st.count;
-    for (int64_t wl = 0; wl < chunk_nwin; wl++) {
+    for (int64_t wl = 0; wl < n_process; wl++) {
         const double2* bw = band + ((int64_t)s * chunk_nwin + wl) * nband;
         for (int c = 0; c < nband; c++) {
             const int j = band_lo + c;
@@ -286,13 +287,37 @@ __global__ void tracker_kernel(const double2* __restrict__ band, int32_t band_lo
 }
 
 cudaError_t launch_tracker(const double2* band, int32_t band_lo, int32_t nband, int32_t n_series,
-                           int64_t chunk_nwin, int64_t win_offset, int64_t nwin, int32_t N, double tol,
-                           int32_t max_inactive, TrackerState* states, int32_t* trk_index, double* trk_period,
-                           cudaStream_t stream) {
+                           int64_t chunk_nwin, int64_t n_process, int64_t win_offset, int64_t nwin, int32_t N,
+                           double tol, int32_t max_inactive, TrackerState* states, int32_t* trk_index,
+                           double* trk_period, cudaStream_t stream) {
     const int threads = 32;
     tracker_kernel<<<(n_series + threads - 1) / threads, threads, 0, stream>>>(
-        band, band_lo, nband, n_series, chunk_nwin, win_offset, nwin, N, tol, max_inactive, states, trk_index,
-        trk_period);
+        band, band_lo, nband, n_series, chunk_nwin, n_process, win_offset, nwin, N, tol, max_inactive, states,
+        trk_index, trk_period);
+    return cudaGetLastError();
+}
+
+// Once the tracker STRUCTURE has reached its fixed point (see tracker_fixed_point in ws_abi.cu) the
+// twelve slots of every later bar repeat those of bar `last`: one coalesced broadcast.
+__global__ void tracker_fill_kernel(int32_t n_series, int64_t nwin, int64_t last, int32_t* __restrict__ trk_index,
+                                    double* __restrict__ trk_period) {
+    const int s = blockIdx.y;
+    const int64_t base = (int64_t)s * nwin * 12;
+    const int64_t total = (nwin - 1 - last) * 12;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i % 12);
+        trk_index[base + (last + 1) * 12 + i] = trk_index[base + last * 12 + q];
+        trk_period[base + (last + 1) * 12 + i] = trk_period[base + last * 12 + q];
+    }
+}
+
+cudaError_t launch_tracker_fill(int32_t n_series, int64_t nwin, int64_t last, int32_t* trk_index,
+                                double* trk_period, cudaStream_t stream) {
+    if (last >= nwin - 1) return cudaSuccess;
+    int64_t blocks = ((nwin - 1 - last) * 12 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    dim3 grid((unsigned)blocks, (unsigned)n_series);
+    tracker_fill_kernel<<<grid, 256, 0, stream>>>(n_series, nwin, last, trk_index, trk_period);
     return cudaGetLastError();
 }
 

@@ -27,9 +27,11 @@ struct TrackerState {
     int32_t bars_inactive[kTrackerCap];
 };
 cudaError_t launch_tracker(const double2* band, int32_t band_lo, int32_t nband, int32_t n_series,
-                           int64_t chunk_nwin, int64_t win_offset, int64_t nwin, int32_t N, double tol,
-                           int32_t max_inactive, TrackerState* states, int32_t* trk_index, double* trk_period,
-                           cudaStream_t stream);
+                           int64_t chunk_nwin, int64_t n_process, int64_t win_offset, int64_t nwin, int32_t N,
+                           double tol, int32_t max_inactive, TrackerState* states, int32_t* trk_index,
+                           double* trk_period, cudaStream_t stream);
+cudaError_t launch_tracker_fill(int32_t n_series, int64_t nwin, int64_t last, int32_t* trk_index,
+                                double* trk_period, cudaStream_t stream);
 
 // ws_window_fft.cu
 cudaError_t launch_window_fft(Params p, cudaStream_t stream);

@@ -25,6 +25,9 @@ def run(name, n, series, bars, outputs, **over):
     if outputs & br.OUT_KALMAN: bufs["kalman"] = torch.empty((series, nwin), dtype=torch.float64, device="cuda")
     if outputs & br.OUT_PHASE: bufs["phase"] = torch.empty((series, nwin, 3, n // 2), dtype=torch.float64, device="cuda")
     if outputs & br.OUT_WKALMAN: bufs["wkalman"] = torch.empty((series, nwin), dtype=torch.float64, device="cuda")
+    if outputs & br.OUT_TRACKER:
+        bufs["trk_index"] = torch.empty((series, nwin, 12), dtype=torch.int32, device="cuda")
+        bufs["trk_period"] = torch.empty((series, nwin, 12), dtype=torch.float64, device="cuda")
     ptrs = {k: v.data_ptr() for k, v in bufs.items()}
     for _ in range(2):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -52,4 +55,9 @@ run("C4 phase chain", 1024, 2, 50000, PH, window_type=br.WINDOW_HANN)
 run("C5 N=4096 K=4 rows", 4096, 2, 200000, R, top_k=4, min_period=9.0, max_period=200.0)
 run("C5 N=4096 K=4 spectra+rows", 4096, 2, 200000, S | R, top_k=4, min_period=9.0, max_period=200.0)
 run("PLA feed + FFT", 1024, 1, 30000, S | B, feed=br.FEED_PLA)
+TR = br.OUT_TRACKER
+run("C3 tracker slots only", 2048, 16, 200000, TR, min_period=18.0, max_period=52.0, detrend=br.DETREND_IIR,
+    trend_period=1024.0, window_type=br.WINDOW_BLACKMAN)
+run("C3 tracker + bins", 2048, 4, 100000, TR | B, min_period=18.0, max_period=52.0, detrend=br.DETREND_IIR,
+    trend_period=1024.0, window_type=br.WINDOW_BLACKMAN)
 br.gpu_shutdown()
