@@ -137,8 +137,7 @@ __device__ __forceinline__ void warp_select_emit(const Params& p, double* pw, co
 // 128-bit stores (rows of consecutive windows are contiguous in the output plane).
 //
 // pw    : shared, [wpb][band] powers of the wpb windows of this batch (destroyed)
-// xb    : shared, [wpb][band] complex bins (band-relative index); nullptr = read the selected
-//         bins back from p.spectra
+// xb    : shared, [wpb][band] complex bins (band-relative index)
 // lo    : first bin of the band;  nvalid : windows of the batch that exist (<= wpb)
 // gw0   : global window index of the batch's first window (series * nwin + window)
 // stage : shared, per-warp scratch of 32 * 16 doubles (used when row_stride <= 16)
@@ -227,13 +226,7 @@ __device__ __forceinline__ void warp_select_emit_batch(const Params& p, double* 
     const bool has_row = live && l < K;
     const int my_bin = my_pos >= 0 ? lo + my_pos : -1;
     double re = 0.0, im = 0.0;
-    if (has_row && my_pos >= 0) {
-        // captured complex bins, or (warp-specialised kernel) the spectrum this CTA has just
-        // written to HBM: read back through L2
-        const double2 x = xb ? xbb[my_pos]
-                             : __ldcg(reinterpret_cast<const double2*>(p.spectra) + (gw0 + g) * (int64_t)(N / 2) + lo + my_pos);
-        re = x.x; im = x.y;
-    }
+    if (has_row && my_pos >= 0) { const double2 x = xbb[my_pos]; re = x.x; im = x.y; }
     const int64_t slot = (gw0 + g) * K + l;
     if (has_row) {
         if (p.bins) p.bins[slot] = my_bin;

@@ -14,7 +14,11 @@
 //   4. the top pass produces the N/2 complex bins of each window in registers and streams them
 //      to HBM with 128-bit stores (a warp writes contiguous 512-byte runs); in-band bins are
 //      also captured in shared memory;
-//   5. one warp per window runs the top-K epilogue (ws_epilogue.cuh) on the captured band.
+//   5. the warps run the batched top-K epilogue (ws_epilogue.cuh: four windows per warp, eight
+//      lanes each at K <= 8) on the captured band and stream the rows out; the selection-sort
+//      rule and K > 8 take the one-warp-per-window form.  Alternatively (WAVESPEC_SPLIT=1, and
+//      always for the tracker plane) the in-band bins go to a compact global buffer consumed by
+//      ws_rows.cu / the tracker kernel.
 //
 // Roofline: the only mandatory HBM traffic is 8*hop bytes in + 8*N bytes out per spectrum; the
 // arithmetic is ~N/2 packed butterflies per window (~4.6 kflop-instr at N = 1024), far below the
@@ -39,7 +43,7 @@ struct SlideLayout {
     int xb_off;         // band capture [T][band] complex
     int ov_off;         // epilogue overlay (CTA epilogue buffers, or pw + ord of the per-window path)
     int band;           // captured bins per window
-    int cta_epi;        // 2: batched warp epilogue (insertion rule); 0: warp-per-window path (sort rule)
+    int epi_mode;        // 2: batched warp epilogue (insertion rule); 0: warp-per-window path (sort rule)
     int Lg;             // lanes per window of the batched warp epilogue
     int total_bytes;
 };
@@ -151,7 +155,7 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     }
     const int band = lay.band, lo = top.lo;
     unsigned char* ov = smem_raw + lay.ov_off;
-    if (lay.cta_epi == 2) {
+    if (lay.epi_mode == 2) {
         // insertion rule, several windows per warp (ws_epilogue.cuh)
         double* pwa = reinterpret_cast<double*>(ov);
         const int pws = lay.Lg == 8 ? 64 : band;          // padded rows for the unrolled epilogue
@@ -220,16 +224,16 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
     // below level 3, otherwise it gets its own space after the work area.  The epilogue buffers
     // are used after the barrier that follows the top pass: they overlay the (dead) work area.
     const int warps = kSlideThreads / 32;
-    lay.cta_epi = 0;
+    lay.epi_mode = 0;
     lay.Lg = 32;
     if (p.select == 0) {
         int need = p.K > (lay.band + 7) / 8 ? p.K : (lay.band + 7) / 8;   // >= K lanes, <= 8 bins per lane
         lay.Lg = 1;
         while (lay.Lg < need && lay.Lg < 32) lay.Lg <<= 1;
-        lay.cta_epi = 2;
+        lay.epi_mode = 2;
     }
     int ov_bytes;
-    if (lay.cta_epi == 2) {
+    if (lay.epi_mode == 2) {
         ov_bytes = ((pl.T * (lay.Lg == 8 ? 64 : lay.band) * 8 + 15) & ~15) + warps * 512 * 8;
     } else {
         ov_bytes = pl.T * lay.band * 8 + warps * lay.band * 4;
