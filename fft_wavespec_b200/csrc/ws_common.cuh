@@ -41,6 +41,7 @@ struct Params {
     double2* band_buf;         // scratch [n_series][chunk_nwin][band]: in-band bins handed from the
                                // sliding kernel to the rows kernel (ws_rows.cu), or nullptr
     int32_t tile_windows;      // windows per CTA tile
+    int32_t k1_wpc_cap;        // per-window FFT: max windows transformed concurrently by a CTA
 };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {

@@ -13,12 +13,14 @@
 //
 // The transform uses exact table twiddles, not the reference's multiplicative recurrence
 // (Legacy/WaveSpecZZ_1.0.2.mq5:955-970): results agree to ~1e-14 relative, inside the 1e-9 bar.
+#include <cstdio>
+#include <cstdlib>
 #include "ws_common.cuh"
 #include "ws_epilogue.cuh"
 
 namespace ws {
 
-// CTA size: 128 threads, 256 for N >= 1024 (one radix-4 butterfly per thread and pass)
+// CTA size: 256 threads; up to 8 windows in flight per CTA below N = 1024, 4 from there on
 
 // prologue value of sample n of a window starting at tile offset `off`
 struct Prologue {
@@ -150,7 +152,7 @@ window_fft_kernel(const Params p) {
     const int q = M >> 3;                          // butterflies per window per radix-8 pass
     int wpc = q > 0 ? kThreads / q : kThreads;
     if (wpc < 1) wpc = 1;
-    if (wpc > 4) wpc = 4;
+    if (wpc > p.k1_wpc_cap) wpc = p.k1_wpc_cap;
 
     // shared layout: tile[Lt_max] | delta[T] | bufA[wpc*M] | bufB[wpc*M] | ord[wpc*M] ints
     const bool from_feed = p.feed != nullptr;
@@ -348,7 +350,7 @@ size_t window_fft_smem_bytes(const Params& p, int tile_windows, int kThreads) {
     int q = M / 8;
     int wpc = q > 0 ? kThreads / q : kThreads;
     if (wpc < 1) wpc = 1;
-    if (wpc > 4) wpc = 4;
+    if (wpc > p.k1_wpc_cap) wpc = p.k1_wpc_cap;
     size_t Lt = p.feed ? (size_t)wpc * N : (size_t)(tile_windows - 1) * p.hop + N;
     size_t doubles = ((Lt + 1) & ~(size_t)1) + ((tile_windows + 1) & ~1);
     size_t bytes = doubles * 8 + 2 * (size_t)wpc * M * 16;
@@ -364,7 +366,7 @@ int window_fft_pick_tile(const Params& p, int kThreads) {
     int q = M / 8;
     int wpc = q > 0 ? kThreads / q : kThreads;
     if (wpc < 1) wpc = 1;
-    if (wpc > 4) wpc = 4;
+    if (wpc > p.k1_wpc_cap) wpc = p.k1_wpc_cap;
     if (p.feed) return wpc;
     long budget = N <= 1024 ? 4096 : N + 63;      // doubles (large N: keep shared memory for a third CTA)
     if (N >= 8192) budget = N;                    // shared memory is full: one window per tile
@@ -394,7 +396,17 @@ static cudaError_t launch_nt(Params p, cudaStream_t stream) {
 }
 
 cudaError_t launch_window_fft(Params p, cudaStream_t stream) {
-    return p.N >= 1024 ? launch_nt<256>(p, stream) : launch_nt<128>(p, stream);
+    // WAVESPEC_K1="threads,wpc" overrides the CTA size and the concurrent-window cap (tuning hook)
+    static int env_nt = -1, env_wpc = 0;
+    if (env_nt < 0) {
+        env_nt = 0;
+        if (const char* e = getenv("WAVESPEC_K1")) sscanf(e, "%d,%d", &env_nt, &env_wpc);
+    }
+    // measured (profiles/README.md): 256 threads everywhere; 8 concurrent windows below N = 1024
+    p.k1_wpc_cap = env_wpc > 0 ? env_wpc : (p.N >= 1024 ? 4 : 8);
+    int nt = env_nt > 0 ? env_nt : 256;
+    if (nt >= 512) return launch_nt<512>(p, stream);
+    return nt >= 256 ? launch_nt<256>(p, stream) : launch_nt<128>(p, stream);
 }
 
 }  // namespace ws
