@@ -17,6 +17,7 @@ OUT = os.path.join(HERE, "libwavespec.so")
 SOURCES = [
     ("ws_abi.cu", []),
     ("ws_window_fft.cu", []),
+    ("ws_window_fft_warp.cu", []),
     ("ws_sliding.cu", []),
     ("ws_rows.cu", []),
     ("ws_inverse.cu", []),

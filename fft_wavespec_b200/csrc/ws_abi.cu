@@ -322,9 +322,8 @@ int run_pipeline(const double* d_series, int32_t n_series, int32_t series_len,
             if (any_spectral) {
                 Params q = p;
                 q.feed = tmp_feed.as<double>(); q.win_offset = wa; q.chunk_nwin = cn;
-                WS_CUDA(ws::launch_window_fft(q, st), "window_fft kernel");
+                WS_CUDA(ws::launch_window_fft(q, st, &g_last_kernel), "window_fft kernel");
                 g_launches++;
-                g_last_kernel = "window_fft";
             }
             WS_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize(pla chunk)");
         }
@@ -395,8 +394,7 @@ int run_pipeline(const double* d_series, int32_t n_series, int32_t series_len,
                 }
                 g_last_kernel = "sliding_shared";
             } else {
-                WS_CUDA(ws::launch_window_fft(p, st), "window_fft kernel");
-                g_last_kernel = "window_fft";
+                WS_CUDA(ws::launch_window_fft(p, st, &g_last_kernel), "window_fft kernel");
             }
             g_launches++;
         }
@@ -498,9 +496,8 @@ int run_tracker_path(Params p, const wavespec_pipeline_cfg* c, int32_t* d_trk_in
             if (sel) { WS_CUDA(ws::launch_rows_from_band(q, st), "rows_from_band kernel"); g_launches++; }
             g_last_kernel = "sliding_shared";
         } else {
-            WS_CUDA(ws::launch_window_fft(q, st), "window_fft kernel");
+            WS_CUDA(ws::launch_window_fft(q, st, &g_last_kernel), "window_fft kernel");
             g_launches++;
-            g_last_kernel = "window_fft";
         }
         if (wa < walk) {
             const int64_t np = (wa + q.chunk_nwin <= walk) ? q.chunk_nwin : walk - wa;

@@ -22,12 +22,14 @@ __device__ __forceinline__ void warp_argbest(double& p, int& pos) {
     }
 }
 
-// pw  : shared, N/2 powers of this window (destroyed: selected entries are overwritten)
-// X   : shared, N/2 complex bins of this window
-// ord : shared int scratch of >= band entries (only used by the SORT rule)
-// gw  : global window index = series * nwin + window
-__device__ __forceinline__ void warp_select_emit(const Params& p, double* pw, const double2* X,
-                                                 int* ord, int64_t gw) {
+// pw   : shared, powers of this window indexed by bin; only [band_lo, band_hi] is touched
+//        (destroyed: selected entries are overwritten)
+// getX : bin -> complex value of this window (called for the K selected bins only)
+// ord  : shared int scratch of >= band entries (only used by the SORT rule)
+// gw   : global window index = series * nwin + window
+template <class GetX>
+__device__ __forceinline__ void warp_select_emit_x(const Params& p, double* pw, GetX getX,
+                                                   int* ord, int64_t gw) {
     const int lane = threadIdx.x & 31;
     const int N = p.N;
     const int K = p.K;
@@ -83,7 +85,7 @@ __device__ __forceinline__ void warp_select_emit(const Params& p, double* pw, co
         const int64_t slot = gw * K + lane;
         if (p.bins) p.bins[slot] = my_bin;
         double re = 0.0, im = 0.0;
-        if (my_bin >= 0) { double2 x = X[my_bin]; re = x.x; im = x.y; }
+        if (my_bin >= 0) { double2 x = getX(my_bin); re = x.x; im = x.y; }
         const double nn = (double)(N - 1);
         if (p.waves) {
             double wv = 0.0;
@@ -129,6 +131,12 @@ __device__ __forceinline__ void warp_select_emit(const Params& p, double* pw, co
     }
 }
 
+
+// X : shared, N/2 complex bins of this window
+__device__ __forceinline__ void warp_select_emit(const Params& p, double* pw, const double2* X,
+                                                 int* ord, int64_t gw) {
+    warp_select_emit_x(p, pw, [X](int b) { return X[b]; }, ord, gw);
+}
 
 // ---- batched form of the insertion rule (A7a): several windows per warp ------------------------
 // The warp is split into groups of Lg lanes (Lg a power of two >= K); each group owns one window,

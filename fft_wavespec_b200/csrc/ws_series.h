@@ -33,8 +33,13 @@ cudaError_t launch_tracker(const double2* band, int32_t band_lo, int32_t nband, 
 cudaError_t launch_tracker_fill(int32_t n_series, int64_t nwin, int64_t last, int32_t* trk_index,
                                 double* trk_period, cudaStream_t stream);
 
-// ws_window_fft.cu
-cudaError_t launch_window_fft(Params p, cudaStream_t stream);
+// ws_window_fft.cu: dispatches to the warp-per-window kernel when it serves the request; the name of
+// the kernel that ran ("window_fft" or "window_fft_warp") is returned through *which when non-null
+cudaError_t launch_window_fft(Params p, cudaStream_t stream, const char** which = nullptr);
+
+// ws_window_fft_warp.cu
+bool window_fft_warp_supported(const Params& p);
+cudaError_t launch_window_fft_warp(Params p, cudaStream_t stream);
 
 // ws_sliding.cu
 bool sliding_shared_supported(const Params& p);

@@ -17,26 +17,12 @@
 #include <cstdlib>
 #include "ws_common.cuh"
 #include "ws_epilogue.cuh"
+#include "ws_window_prologue.cuh"
+#include "ws_series.h"
 
 namespace ws {
 
 // CTA size: 256 threads; up to 8 windows in flight per CTA below N = 1024, 4 from there on
-
-// prologue value of sample n of a window starting at tile offset `off`
-struct Prologue {
-    const double* tile;     // shared: x (or x - y for the IIR detrend)
-    const double* wtab;     // global window table or nullptr
-    const double* apow;     // global alpha^j or nullptr
-    double sub;             // mean (DETREND_MEAN) or delta_w (DETREND_IIR)
-    int mode;
-    __device__ __forceinline__ double operator()(int off, int n) const {
-        double v = tile[off + n];
-        if (mode == 2) v = v - sub;
-        else if (mode == 1) v = v - __ldg(apow + n) * sub;
-        if (wtab) v = v * __ldg(wtab + n);
-        return v;
-    }
-};
 
 __device__ __forceinline__ void r4_butterfly(double2& a0, double2& a1, double2& a2, double2& a3) {
     double2 b0 = cadd(a0, a2), b1 = csub(a0, a2), b2 = cadd(a1, a3);
@@ -99,44 +85,15 @@ __device__ __forceinline__ void stockham_pass(Load load, double2* out, int nw, i
     }
 }
 
-// Trend IIR of Legacy/...-kalman-fast.mq5:3367-3379 over x[0..L): y[0] = c (x0 + x0),
-// y[a] = c (x[a] + x[a-1]) + alpha y[a-1].  Blocked over the CTA: local recurrences from zero,
-// a serial carry pass over the kThreads chunk ends, then the alpha^k fix-up.  Differs from the
-// serial loop by rounding only (a few ulp of y).
-template <int kThreads>
-__device__ void cta_trend_iir(const double* x, int L, double al, double c, double* y, double* carry) {
-    const int tid = threadIdx.x;
-    const int chunk = (L + kThreads - 1) / kThreads;
-    const int a0 = tid * chunk;
-    double acc = 0.0;
-    for (int a = a0; a < a0 + chunk && a < L; a++) {
-        double u = (a == 0) ? c * (x[0] + x[0]) : c * (x[a] + x[a - 1]);
-        acc = u + al * acc;
-        y[a] = acc;
-    }
-    carry[tid] = acc;
-    __syncthreads();
-    if (tid == 0) {
-        double ac = pow(al, (double)chunk);
-        double run = 0.0;
-        for (int t = 0; t < kThreads; t++) {
-            double e = carry[t];
-            carry[t] = run;                 // carry-in of chunk t
-            run = e + ac * run;
-        }
-    }
-    __syncthreads();
-    double cin = carry[tid];
-    double f = al;
-    for (int a = a0; a < a0 + chunk && a < L; a++) { y[a] = y[a] + f * cin; f *= al; }
-    __syncthreads();
-}
-
-template <int kThreads>
+// LN = log2 of the window length baked in at compile time (0: run-time N); CAP likewise for the
+// concurrent-window cap.  With LN fixed every index split below is a shift and the pass loop
+// unrolls; the run-time variant pays an integer division per element (ncu: 4x the FP64 work).
+template <int kThreads, int LN, int CAP>
 __global__ void __launch_bounds__(kThreads)
 window_fft_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = p.N, M = N >> 1;
+    const int N = LN ? (1 << LN) : p.N, M = N >> 1;
+    const int log2N = LN ? LN : p.log2N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = p.tile_windows;
     const int64_t w0 = p.win_offset + (int64_t)blockIdx.x * T;
@@ -152,7 +109,8 @@ window_fft_kernel(const Params p) {
     const int q = M >> 3;                          // butterflies per window per radix-8 pass
     int wpc = q > 0 ? kThreads / q : kThreads;
     if (wpc < 1) wpc = 1;
-    if (wpc > p.k1_wpc_cap) wpc = p.k1_wpc_cap;
+    const int cap = CAP ? CAP : p.k1_wpc_cap;
+    if (wpc > cap) wpc = cap;
 
     // shared layout: tile[Lt_max] | delta[T] | bufA[wpc*M] | bufB[wpc*M] | ord[wpc*M] ints
     const bool from_feed = p.feed != nullptr;
@@ -235,7 +193,7 @@ window_fft_kernel(const Params p) {
                             pro_mode ? delta[wb + wl] : 0.0, pro_mode};
                 return make_double2(pr(off, 2 * m), pr(off, 2 * m + 1));
             };
-            int rem = p.log2N - 1;                   // log2 M
+            int rem = log2N - 1;                     // log2 M
             int Ns = 1;
             bool first = true;
             if (rem == 0) {                          // M = 1 (N = 2): nothing to transform
@@ -243,7 +201,10 @@ window_fft_kernel(const Params p) {
                 __syncthreads();
                 double2* t = in; in = out; out = t;
             }
-            while (rem > 0) {
+            constexpr int kUnroll = LN ? 5 : 1;      // 5 passes cover log2 M <= 13
+#pragma unroll kUnroll
+            for (int pass = 0; pass < 5; pass++) {
+                if (rem <= 0) break;
                 const int lr = rem >= 3 ? 3 : rem;
                 const double2* src = in;
                 auto from_buf = [&](int wl, int m) { return src[(size_t)wl * M + m]; };
@@ -379,34 +340,51 @@ int window_fft_pick_tile(const Params& p, int kThreads) {
     return (int)t;
 }
 
-template <int NT>
+template <int NT, int LN, int CAP>
 static cudaError_t launch_nt(Params p, cudaStream_t stream) {
     p.tile_windows = window_fft_pick_tile(p, NT);
     size_t smem = window_fft_smem_bytes(p, p.tile_windows, NT);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(window_fft_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        cudaError_t e = cudaFuncSetAttribute(window_fft_kernel<NT, LN, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     if (smem > 232448) return cudaErrorInvalidValue;
     dim3 grid((unsigned)((p.chunk_nwin + p.tile_windows - 1) / p.tile_windows), (unsigned)p.n_series);
-    window_fft_kernel<NT><<<grid, NT, smem, stream>>>(p);
+    window_fft_kernel<NT, LN, CAP><<<grid, NT, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_window_fft(Params p, cudaStream_t stream) {
-    // WAVESPEC_K1="threads,wpc" overrides the CTA size and the concurrent-window cap (tuning hook)
+cudaError_t launch_window_fft(Params p, cudaStream_t stream, const char** which) {
+    if (which) *which = "window_fft";
+    // WAVESPEC_K1="threads,wpc" selects the run-time-N kernel with that CTA size and
+    // concurrent-window cap (tuning hook)
     static int env_nt = -1, env_wpc = 0;
     if (env_nt < 0) {
         env_nt = 0;
         if (const char* e = getenv("WAVESPEC_K1")) sscanf(e, "%d,%d", &env_nt, &env_wpc);
     }
-    // measured (profiles/README.md): 256 threads everywhere; 8 concurrent windows below N = 1024
-    p.k1_wpc_cap = env_wpc > 0 ? env_wpc : (p.N >= 1024 ? 4 : 8);
-    int nt = env_nt > 0 ? env_nt : 256;
-    if (nt >= 512) return launch_nt<512>(p, stream);
-    return nt >= 256 ? launch_nt<256>(p, stream) : launch_nt<128>(p, stream);
+    if (env_nt > 0) {
+        p.k1_wpc_cap = env_wpc > 0 ? env_wpc : 4;
+        if (env_nt >= 512) return launch_nt<512, 0, 0>(p, stream);
+        return env_nt >= 256 ? launch_nt<256, 0, 0>(p, stream) : launch_nt<128, 0, 0>(p, stream);
+    }
+    if (window_fft_warp_supported(p)) {
+        if (which) *which = "window_fft_warp";
+        return launch_window_fft_warp(p, stream);
+    }
+    // measured (profiles/README.md): 256 threads everywhere; 8 concurrent windows below N = 1024.
+    // The window lengths of BASELINE.json's configs get compile-time-N instances.
+    p.k1_wpc_cap = p.N >= 1024 ? 4 : 8;
+    switch (p.N) {
+        case 256:  return launch_nt<256, 8, 8>(p, stream);
+        case 512:  return launch_nt<256, 9, 8>(p, stream);
+        case 1024: return launch_nt<256, 10, 4>(p, stream);
+        case 2048: return launch_nt<256, 11, 4>(p, stream);
+        case 4096: return launch_nt<256, 12, 4>(p, stream);
+        default:   return launch_nt<256, 0, 0>(p, stream);
+    }
 }
 
 }  // namespace ws
