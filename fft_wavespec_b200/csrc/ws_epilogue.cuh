@@ -14,6 +14,19 @@ constexpr double kPi = 3.14159265358979323846;
 
 // warp-wide argmax of (p, pos) under `better`; every lane returns the winner.
 __device__ __forceinline__ void warp_argbest(double& p, int& pos) {
+    // Fast path: the high word of a non-negative double orders like the double.  When exactly one
+    // lane holds the maximal high word that lane is the strict winner: one REDUX, one VOTE and
+    // three shuffles instead of the 5-stage ladder.  Ties in the top 32 bits (or no candidate at
+    // all) take the full comparison below; both conditions are warp-uniform.
+    const int hi = (p >= 0.0) ? __double2hiint(p) + 1 : 0;          // 0: no candidate (-1, -2, NaN)
+    const int mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned cand = __ballot_sync(0xffffffffu, hi == mh);
+    if (mh != 0 && (cand & (cand - 1)) == 0) {
+        const int src = __ffs(cand) - 1;
+        p = __shfl_sync(0xffffffffu, p, src);
+        pos = __shfl_sync(0xffffffffu, pos, src);
+        return;
+    }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
         double op = shfl_xor_d(p, m);

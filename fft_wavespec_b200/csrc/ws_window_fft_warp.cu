@@ -115,10 +115,22 @@ window_fft_warp_kernel(const Params p, const WarpLayout L) {
         } else if (p.detrend == 1) {
             sub = delta[t];
         }
-        const Prologue pr{tile, p.has_window ? p.wtab : nullptr, p.apow, sub, p.detrend};
-        auto from_tile = [&](int m) { return make_double2(pr(off, 2 * m), pr(off, 2 * m + 1)); };
-
-        ws_wf::dif_pass<LN, G::radix(0), G::stride(0), true>(lane, from_tile, Z, tw);
+        // pass 0 reads the tile through the prologue; one instance per (detrend, window) case so
+        // the per-sample code carries no mode branches
+        const double2* wt2 = reinterpret_cast<const double2*>(p.wtab);
+        const double2* ap2 = reinterpret_cast<const double2*>(p.apow);
+#define WS_PASS0(MODE, WIN)                                                                       \
+        {                                                                                         \
+            const ProloguePair<MODE, WIN> pr{tile, wt2, ap2, sub};                                \
+            ws_wf::dif_pass<LN, G::radix(0), G::stride(0), true>(                                 \
+                lane, [&](int m) { return pr(off, m); }, Z, tw);                                  \
+        }
+        if (p.has_window) {
+            if (p.detrend == 1) WS_PASS0(1, true) else if (p.detrend == 2) WS_PASS0(2, true) else WS_PASS0(0, true)
+        } else {
+            if (p.detrend == 1) WS_PASS0(1, false) else if (p.detrend == 2) WS_PASS0(2, false) else WS_PASS0(0, false)
+        }
+#undef WS_PASS0
         ws_wf::later_passes<LN, 1>(lane, Z, tw, warp_sync);
         __syncwarp();
 

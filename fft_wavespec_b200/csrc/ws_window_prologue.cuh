@@ -21,6 +21,24 @@ struct Prologue {
     }
 };
 
+// Same arithmetic with the detrend mode and the presence of a window table fixed at compile time,
+// on the sample PAIR (2m, 2m+1) that forms one complex input: the tables are read as one 16-byte
+// load per pair (they are cudaMalloc'ed, so element 2m is 16-byte aligned).
+template <int MODE, bool WIN>
+struct ProloguePair {
+    const double* tile;
+    const double2* wtab2;
+    const double2* apow2;
+    double sub;
+    __device__ __forceinline__ double2 operator()(int off, int m) const {
+        double2 v = make_double2(tile[off + 2 * m], tile[off + 2 * m + 1]);
+        if (MODE == 2) { v.x = v.x - sub; v.y = v.y - sub; }
+        else if (MODE == 1) { const double2 a = __ldg(apow2 + m); v.x = v.x - a.x * sub; v.y = v.y - a.y * sub; }
+        if (WIN) { const double2 w = __ldg(wtab2 + m); v.x = v.x * w.x; v.y = v.y * w.y; }
+        return v;
+    }
+};
+
 // Trend IIR of Legacy/...-kalman-fast.mq5:3367-3379 over x[0..L): y[0] = c (x0 + x0),
 // y[a] = c (x[a] + x[a-1]) + alpha y[a-1].  Blocked over the CTA: local recurrences from zero,
 // a serial carry pass over the kThreads chunk ends, then the alpha^k fix-up.  Differs from the
