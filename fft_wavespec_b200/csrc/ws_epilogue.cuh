@@ -79,6 +79,24 @@ __device__ __forceinline__ void warp_select_emit_x(const Params& p, double* pw, 
             __syncwarp();
             if (lane == r) { my_bin = sel; my_pow = bp; }
         }
+    } else if (hi - lo < 64) {
+        // narrow band (the usual case): each lane keeps its two candidates in registers, so a
+        // round is a compare, the warp argmax and a conditional retire — no shared-memory traffic.
+        // NaN powers never win (as in the scan below): they are retired up front.
+        const int b0 = lo + lane, b1 = lo + 32 + lane;
+        double v0 = -2.0, v1 = -2.0;
+        if (b0 <= hi) { v0 = pw[b0]; if (!(v0 >= 0.0)) v0 = -2.0; }
+        if (b1 <= hi) { v1 = pw[b1]; if (!(v1 >= 0.0)) v1 = -2.0; }
+        for (int r = 0; r < K; r++) {
+            double bp = v0; int bpos = b0;
+            if (v1 > bp) { bp = v1; bpos = b1; }
+            if (bp < 0.0) { bp = -1.0; bpos = 0x7fffffff; }
+            warp_argbest(bp, bpos);
+            if (bpos == 0x7fffffff) break;              // band exhausted: remaining slots stay -1
+            if (bpos == b0) v0 = -2.0;
+            if (bpos == b1) v1 = -2.0;
+            if (lane == r) { my_bin = bpos; my_pow = bp; }
+        }
     } else {
         for (int r = 0; r < K; r++) {
             double bp = -1.0; int bpos = 0x7fffffff;

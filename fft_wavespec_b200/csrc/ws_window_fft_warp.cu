@@ -23,7 +23,6 @@
 
 namespace ws {
 
-constexpr int kWarps = 8;
 
 struct WarpLayout {
     int tile_doubles;     // staged samples (even)
@@ -31,7 +30,7 @@ struct WarpLayout {
     size_t z_off, pw_off, ord_off, total;
 };
 
-static WarpLayout warp_layout(const Params& p, int T) {
+static WarpLayout warp_layout(const Params& p, int T, int kWarps) {
     WarpLayout L;
     const int M = p.N / 2;
     const int Lt = (T - 1) * p.hop + p.N;
@@ -50,8 +49,9 @@ static WarpLayout warp_layout(const Params& p, int T) {
     return L;
 }
 
-template <int LN>
-__global__ void __launch_bounds__(kWarps * 32)
+// kWarps warps per CTA, at least MINB CTAs per SM (bounds the registers)
+template <int LN, int kWarps, int MINB>
+__global__ void __launch_bounds__(kWarps * 32, MINB)
 window_fft_warp_kernel(const Params p, const WarpLayout L) {
     typedef ws_wf::Geo<LN> G;
     constexpr int N = G::N, M = G::M;
@@ -154,53 +154,63 @@ window_fft_warp_kernel(const Params p, const WarpLayout L) {
     }
 }
 
-static int warp_pick_tile(const Params& p) {
+static int warp_pick_tile(const Params& p, int kWarps) {
     // 64 windows per tile when the staged samples stay within 4096 + N doubles; strided batches
     // (hop ~ N) get at least one window per warp while the tile fits 12288 doubles
     long budget = 4096 + p.N;
     long t = (budget - p.N) / p.hop + 1;
     if (t < kWarps && (long)(kWarps - 1) * p.hop + p.N <= 12288) t = kWarps;
-    if (t > 64) t = 64;
+    const long cap = 64 - 64 % kWarps + (64 % kWarps ? kWarps : 0);   // multiple of kWarps: no warp idles on a full tile
+    if (t > cap) t = cap;
     if (p.chunk_nwin < t) t = (long)p.chunk_nwin;
     return (int)t;
 }
 
-template <int LN>
+template <int LN, int kWarps, int MINB>
 static cudaError_t launch_ln(Params p, cudaStream_t stream) {
-    p.tile_windows = warp_pick_tile(p);
-    const WarpLayout L = warp_layout(p, p.tile_windows);
+    p.tile_windows = warp_pick_tile(p, kWarps);
+    const WarpLayout L = warp_layout(p, p.tile_windows, kWarps);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(window_fft_warp_kernel<LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        cudaError_t e = cudaFuncSetAttribute(window_fft_warp_kernel<LN, kWarps, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     if (L.total > 232448) return cudaErrorInvalidValue;
     dim3 grid((unsigned)((p.chunk_nwin + p.tile_windows - 1) / p.tile_windows), (unsigned)p.n_series);
-    window_fft_warp_kernel<LN><<<grid, kWarps * 32, L.total, stream>>>(p, L);
+    window_fft_warp_kernel<LN, kWarps, MINB><<<grid, kWarps * 32, L.total, stream>>>(p, L);
     return cudaGetLastError();
 }
 
+// Warps per CTA, measured on B200 (profiles/README.md): 12 warps x 2 CTAs (80 registers) at
+// N = 512, 8 warps x 2 CTAs (128 registers) at N = 1024, 12 warps x 1 CTA at N = 2048.
+// WAVESPEC_K1W=0 (tuning hook) routes everything to the CTA kernel of ws_window_fft.cu.
+static bool warp_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("WAVESPEC_K1W");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+static int warps_for(const Params& p) { return p.N == 1024 ? 8 : 12; }
+
 // true when this kernel serves the request (the caller falls back to ws_window_fft.cu otherwise)
 bool window_fft_warp_supported(const Params& p) {
-    static int enabled = -1;
-    if (enabled < 0) {
-        const char* e = getenv("WAVESPEC_K1W");          // WAVESPEC_K1W=0: tuning hook, old kernel
-        enabled = (e && e[0] == '0') ? 0 : 1;
-    }
-    if (!enabled || p.feed || p.phase) return false;
+    if (!warp_enabled() || p.feed || p.phase) return false;
     if (p.N < 512 || p.N > 2048) return false;    // N = 256: half the lanes idle in the passes, the CTA kernel wins
     if (p.chunk_nwin < 1) return false;
-    const int T = warp_pick_tile(p);
-    if (T < kWarps && p.chunk_nwin >= kWarps) return false;      // tile too wide for a shared stage
-    return warp_layout(p, T).total <= 232448;
+    const int W = warps_for(p);
+    const int T = warp_pick_tile(p, W);
+    if (T < W && p.chunk_nwin >= W) return false;                // tile too wide for a shared stage
+    return warp_layout(p, T, W).total <= 232448;
 }
 
 cudaError_t launch_window_fft_warp(Params p, cudaStream_t stream) {
     switch (p.N) {
-        case 512:  return launch_ln<9>(p, stream);
-        case 1024: return launch_ln<10>(p, stream);
-        case 2048: return launch_ln<11>(p, stream);
+        case 512:  return launch_ln<9, 12, 2>(p, stream);
+        case 1024: return launch_ln<10, 8, 2>(p, stream);
+        case 2048: return launch_ln<11, 12, 1>(p, stream);
         default:   return cudaErrorInvalidValue;
     }
 }
