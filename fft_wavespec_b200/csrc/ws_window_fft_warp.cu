@@ -193,24 +193,32 @@ static bool warp_enabled() {
     }
     return v != 0;
 }
-static int warps_for(const Params& p) { return p.N == 1024 ? 8 : 12; }
+static bool fits(const Params& p, int W) {
+    const int T = warp_pick_tile(p, W);
+    if (T < W && p.chunk_nwin >= W) return false;                // tile too wide for a shared stage
+    return warp_layout(p, T, W).total <= 232448;
+}
+// 0: not served.  N = 2048 drops to 8 warps when a wide band's powers do not fit beside 12 Z arrays.
+static int warps_for(const Params& p) {
+    if (p.N == 1024) return fits(p, 8) ? 8 : 0;
+    if (fits(p, 12)) return 12;
+    return p.N == 2048 && fits(p, 8) ? 8 : 0;
+}
 
 // true when this kernel serves the request (the caller falls back to ws_window_fft.cu otherwise)
 bool window_fft_warp_supported(const Params& p) {
     if (!warp_enabled() || p.feed || p.phase) return false;
     if (p.N < 512 || p.N > 2048) return false;    // N = 256: half the lanes idle in the passes, the CTA kernel wins
     if (p.chunk_nwin < 1) return false;
-    const int W = warps_for(p);
-    const int T = warp_pick_tile(p, W);
-    if (T < W && p.chunk_nwin >= W) return false;                // tile too wide for a shared stage
-    return warp_layout(p, T, W).total <= 232448;
+    return warps_for(p) != 0;
 }
 
 cudaError_t launch_window_fft_warp(Params p, cudaStream_t stream) {
+    const int W = warps_for(p);
     switch (p.N) {
         case 512:  return launch_ln<9, 12, 2>(p, stream);
         case 1024: return launch_ln<10, 8, 2>(p, stream);
-        case 2048: return launch_ln<11, 12, 1>(p, stream);
+        case 2048: return W == 12 ? launch_ln<11, 12, 1>(p, stream) : launch_ln<11, 8, 1>(p, stream);
         default:   return cudaErrorInvalidValue;
     }
 }

@@ -652,3 +652,57 @@ def test_pla_long_windows_direct_render_fallback(br, oracle):
         assert np.array_equal(lines[w], line)
         m = min(st_.size, bounds.shape[1])
         assert np.array_equal(bounds[w, :m, 0], st_[:m]) and np.array_equal(bounds[w, :m, 1], en_[:m])
+
+
+# ---- warp-per-window FFT kernel (ws_window_fft_warp.cu): N = 512 / 1024 / 2048 -------------------
+@pytest.mark.parametrize("n", [512, 1024, 2048])
+@pytest.mark.parametrize("detrend,wtype", [(0, 3), (1, 3), (2, 1), (2, 0), (1, 0), (0, 5)])
+def test_warp_kernel_prologues_match_oracle(br, oracle, n, detrend, wtype):
+    """Every detrend / window combination through the one-warp-per-window kernel, on a window count
+    that leaves a ragged last tile and warps without a window in it."""
+    s = synth.random_walk(900 + n + 7 * detrend + wtype, n + 64 + 64 + 5)
+    cfg = br.default_cfg(n, top_k=8, min_period=18.0, max_period=52.0, detrend=detrend,
+                         trend_period=float(n // 2), window_type=wtype)
+    got, ref = run_both(br, oracle, s, cfg, br.OUT_SPECTRA | br.OUT_BINS | br.OUT_ROWS | br.OUT_WAVES)
+    assert br.last_kernel() == "window_fft_warp"
+    check_planes(br, got, ref, cfg)
+
+
+@pytest.mark.parametrize("n,hop", [(512, 3), (1024, 7), (2048, 2), (512, 512), (1024, 1024), (1024, 300)])
+def test_warp_kernel_hops_and_contiguous_batches(br, oracle, n, hop):
+    nwin = 21
+    s = synth.random_walk(950 + n + hop, n + (nwin - 1) * hop)
+    cfg = br.default_cfg(n, hop=hop, top_k=4, min_period=9.0, max_period=200.0, window_type=br.WINDOW_HANN)
+    got, ref = run_both(br, oracle, s, cfg, br.OUT_SPECTRA | br.OUT_BINS | br.OUT_WAVES)
+    assert got["bins"].shape[0] == nwin
+    assert br.last_kernel() in ("window_fft_warp", "window_fft")   # wide strides may fall back
+    if hop <= 7:
+        assert br.last_kernel() == "window_fft_warp"
+    check_planes(br, got, ref, cfg)
+
+
+@pytest.mark.parametrize("select", [0, 1])
+@pytest.mark.parametrize("band", [(2.0, 1.0e9), (18.0, 52.0), (4.0, 40.0), (3.0, 3.5)])
+def test_warp_kernel_selection_rules_and_band_widths(br, oracle, select, band):
+    """Wide bands take the shared-memory scan, narrow ones the register-resident rounds; the last
+    band is narrower than top_k; both tie rules."""
+    n = 1024
+    s = np.round(synth.random_walk(990, n + 150), 3)          # coarse quantisation: power ties
+    cfg = br.default_cfg(n, top_k=8, min_period=band[0], max_period=band[1], select=select,
+                         detrend=br.DETREND_MEAN, window_type=br.WINDOW_HANN)
+    got, ref = run_both(br, oracle, s, cfg, br.OUT_BINS | br.OUT_ROWS | br.OUT_WAVES | br.OUT_SPECTRA)
+    assert br.last_kernel() == "window_fft_warp"
+    check_planes(br, got, ref, cfg)
+
+
+def test_warp_kernel_many_series_rows_only(br, oracle):
+    """No spectra plane: the split only feeds the selection (and nothing is stored per bin)."""
+    n = 512
+    s = synth.random_walk_batch(1000, 5, n + 700)
+    cfg = br.default_cfg(n, top_k=5, min_period=9.0, max_period=200.0, detrend=br.DETREND_MEAN,
+                         window_type=br.WINDOW_HANN_WIP)
+    got = br.pipeline_host(s, cfg, br.OUT_ROWS | br.OUT_BINS)
+    assert br.last_kernel() == "window_fft_warp"
+    for i in range(s.shape[0]):
+        ref = oracle.pipeline_series(s[i], ocfg_from(oracle, cfg), br.OUT_ROWS | br.OUT_BINS)
+        check_planes(br, {k: (v[i] if v is not None else None) for k, v in got.items()}, ref, cfg)
