@@ -186,82 +186,118 @@ template <int LG>
 __device__ __forceinline__ void warp_select_emit_batch(const Params& p, double* pw, const double2* xb,
                                                        int band, int lo, int Lg_rt, int nvalid, int64_t gw0,
                                                        double* stage) {
-    // LG == 8: pw rows are padded to 64 entries, out-of-band and non-existing windows hold -2, so
-    // the scans load unconditionally
     const int lane = threadIdx.x & 31;
     const int Lg = LG ? LG : Lg_rt;
     const int g = lane / Lg, l = lane - g * Lg;
     const int N = p.N, K = p.K;
-    double* pwb = pw + g * (LG == 8 ? 64 : band);
     const double2* xbb = xb + g * band;
     const bool live = g < nvalid;
 
     double bsum = 0.0;
-    if (LG == 8) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) { const double v = pwb[l + 8 * i]; bsum += (v >= 0.0) ? v : 0.0; }
-#pragma unroll
-        for (int m = 4; m >= 1; m >>= 1) bsum += shfl_xor_d(bsum, m);
-    } else {
-        if (live) for (int e = l; e < band; e += Lg) bsum += pwb[e];
-        for (int m = Lg >> 1; m >= 1; m >>= 1) bsum += shfl_xor_d(bsum, m);
-    }
-
     int my_pos = -1;
     double my_pow = -1.0;
-    for (int r = 0; r < K; r++) {
-        double bp = -1.0; int bpos = 0x7fffffff;
-        // ascending scan inside a lane: an equal power met later never displaces the earlier
-        // (lower) bin, so strict '>' alone implements the tie rule here
-        if (LG == 8) {
+    if (LG == 8) {
+        // K <= 8, band <= 64: a sorting network instead of K dependent argmax rounds.  Lane l of
+        // the group owns band entries l, l+8, .., l+56 (powers straight from the captured bins;
+        // entries past the band, NaNs and windows that do not exist are "absent" = -2), sorts
+        // them (Batcher, 19 compare-exchanges), then three bitonic merges with the lanes at
+        // distance 1, 2, 4 keep the best eight of each union.  Every compare-exchange uses the
+        // full (power desc, bin asc) order, so the result is exactly what the reference's
+        // ascending insertion scan leaves in its top-K list; all eight lanes end with the same
+        // list and lane l takes entry l.  No shared-memory traffic and an 18-stage dependency
+        // chain instead of K x (scan + ladder).
+        double v[8];
+        int e[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            e[i] = l + 8 * i;
+            double q = -2.0;
+            if (live && e[i] < band) { const double2 x = xbb[e[i]]; q = x.x * x.x + x.y * x.y; }
+            if (!(q >= 0.0)) q = -2.0;
+            v[i] = q;
+            bsum += (q >= 0.0) ? q : 0.0;
+        }
+#pragma unroll
+        for (int m = 4; m >= 1; m >>= 1) bsum += shfl_xor_d(bsum, m);
+#define WS_CE(i, j)                                                                     \
+        {                                                                               \
+            const bool sw = better(v[j], e[j], v[i], e[i]);                             \
+            const double a = v[i], b = v[j];                                            \
+            const int ea = e[i], eb = e[j];                                             \
+            v[i] = sw ? b : a; v[j] = sw ? a : b;                                       \
+            e[i] = sw ? eb : ea; e[j] = sw ? ea : eb;                                   \
+        }
+        WS_CE(0, 1) WS_CE(2, 3) WS_CE(4, 5) WS_CE(6, 7)
+        WS_CE(0, 2) WS_CE(1, 3) WS_CE(4, 6) WS_CE(5, 7)
+        WS_CE(1, 2) WS_CE(5, 6)
+        WS_CE(0, 4) WS_CE(1, 5) WS_CE(2, 6) WS_CE(3, 7)
+        WS_CE(2, 4) WS_CE(3, 5)
+        WS_CE(1, 2) WS_CE(3, 4) WS_CE(5, 6)
+#pragma unroll
+        for (int d = 1; d <= 4; d <<= 1) {
+            double pv[8];
+            int pe[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const int e = l + 8 * i;
-                const double v = pwb[e];
-                if (v > bp) { bp = v; bpos = e; }
+                pv[i] = shfl_xor_d(v[7 - i], d);
+                pe[i] = __shfl_xor_sync(0xffffffffu, e[7 - i], d);
             }
-        } else if (live) {
-            for (int e = l; e < band; e += Lg) {
-                double v = pwb[e];
-                if (v > bp) { bp = v; bpos = e; }
-            }
-        }
-        {
-            // Cross-lane argmax of (power desc, position asc) inside the group.  Fast path: the
-            // high word of a non-negative double orders like the double; when exactly one lane
-            // of every group holds the maximal high word that lane is the winner and is simply
-            // broadcast.  Otherwise (ties in the top 32 bits) fall back to the full comparison.
-            const int hi = (bp >= 0.0) ? __double2hiint(bp) + 1 : 0;      // 0 = no candidate
-            int mh = hi;
-            if (LG == 8) {
 #pragma unroll
-                for (int m = 4; m >= 1; m >>= 1) mh = max(mh, __shfl_xor_sync(0xffffffffu, mh, m));
-            } else {
-                for (int m = Lg >> 1; m >= 1; m >>= 1) mh = max(mh, __shfl_xor_sync(0xffffffffu, mh, m));
-            }
-            const unsigned cand = __ballot_sync(0xffffffffu, hi == mh && mh != 0);
-            const unsigned gmask = (Lg == 32 ? 0xffffffffu : ((1u << Lg) - 1u)) << (g * Lg);
-            const unsigned mine = cand & gmask;
-            const bool unique = (mine & (mine - 1)) == 0;                 // 0 or 1 candidate
-            if (__all_sync(0xffffffffu, unique)) {
-                const int srcl = mine ? (__ffs(mine) - 1) : lane;
-                bp = __shfl_sync(0xffffffffu, bp, srcl);
-                bpos = __shfl_sync(0xffffffffu, bpos, srcl);
-                if (!mine) { bp = -1.0; bpos = 0x7fffffff; }
-            } else {
-                for (int m = Lg >> 1; m >= 1; m >>= 1) {
-                    double op = shfl_xor_d(bp, m);
-                    int opos = __shfl_xor_sync(0xffffffffu, bpos, m);
-                    if (better(op, opos, bp, bpos)) { bp = op; bpos = opos; }
+            for (int i = 0; i < 8; i++)
+                if (better(pv[i], pe[i], v[i], e[i])) { v[i] = pv[i]; e[i] = pe[i]; }
+            WS_CE(0, 4) WS_CE(1, 5) WS_CE(2, 6) WS_CE(3, 7)
+            WS_CE(0, 2) WS_CE(1, 3) WS_CE(4, 6) WS_CE(5, 7)
+            WS_CE(0, 1) WS_CE(2, 3) WS_CE(4, 5) WS_CE(6, 7)
+        }
+#undef WS_CE
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (l == i && i < K && v[i] >= 0.0) { my_pos = e[i]; my_pow = v[i]; }
+    } else {
+        double* pwb = pw + g * band;
+        if (live) for (int e = l; e < band; e += Lg) bsum += pwb[e];
+        for (int m = Lg >> 1; m >= 1; m >>= 1) bsum += shfl_xor_d(bsum, m);
+        for (int r = 0; r < K; r++) {
+            double bp = -1.0; int bpos = 0x7fffffff;
+            // ascending scan inside a lane: an equal power met later never displaces the earlier
+            // (lower) bin, so strict '>' alone implements the tie rule here
+            if (live) {
+                for (int e = l; e < band; e += Lg) {
+                    double v = pwb[e];
+                    if (v > bp) { bp = v; bpos = e; }
                 }
             }
-        }
-        if (bpos != 0x7fffffff) {
-            if ((bpos & (Lg - 1)) == l) pwb[bpos] = -2.0;      // the owning lane retires it (-2 < -1)
-            if (l == r) { my_pos = bpos; my_pow = bp; }
+            {
+                // Cross-lane argmax of (power desc, position asc) inside the group.  Fast path: the
+                // high word of a non-negative double orders like the double; when exactly one lane
+                // of every group holds the maximal high word that lane is the winner and is simply
+                // broadcast.  Otherwise (ties in the top 32 bits) fall back to the full comparison.
+                const int hi = (bp >= 0.0) ? __double2hiint(bp) + 1 : 0;      // 0 = no candidate
+                int mh = hi;
+                for (int m = Lg >> 1; m >= 1; m >>= 1) mh = max(mh, __shfl_xor_sync(0xffffffffu, mh, m));
+                const unsigned cand = __ballot_sync(0xffffffffu, hi == mh && mh != 0);
+                const unsigned gmask = (Lg == 32 ? 0xffffffffu : ((1u << Lg) - 1u)) << (g * Lg);
+                const unsigned mine = cand & gmask;
+                const bool unique = (mine & (mine - 1)) == 0;                 // 0 or 1 candidate
+                if (__all_sync(0xffffffffu, unique)) {
+                    const int srcl = mine ? (__ffs(mine) - 1) : lane;
+                    bp = __shfl_sync(0xffffffffu, bp, srcl);
+                    bpos = __shfl_sync(0xffffffffu, bpos, srcl);
+                    if (!mine) { bp = -1.0; bpos = 0x7fffffff; }
+                } else {
+                    for (int m = Lg >> 1; m >= 1; m >>= 1) {
+                        double op = shfl_xor_d(bp, m);
+                        int opos = __shfl_xor_sync(0xffffffffu, bpos, m);
+                        if (better(op, opos, bp, bpos)) { bp = op; bpos = opos; }
+                    }
+                }
+            }
+            if (bpos != 0x7fffffff) {
+                if ((bpos & (Lg - 1)) == l) pwb[bpos] = -2.0;      // the owning lane retires it (-2 < -1)
+                if (l == r) { my_pos = bpos; my_pow = bp; }
+            }
         }
     }
-
     const bool has_row = live && l < K;
     const int my_bin = my_pos >= 0 ? lo + my_pos : -1;
     double re = 0.0, im = 0.0;

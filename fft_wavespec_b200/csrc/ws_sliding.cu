@@ -158,24 +158,19 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     if (lay.epi_mode == 2) {
         // insertion rule, several windows per warp (ws_epilogue.cuh)
         double* pwa = reinterpret_cast<double*>(ov);
-        const int pws = lay.Lg == 8 ? 64 : band;          // padded rows for the unrolled epilogue
-        if (lay.Lg == 8) {
-            for (int i = tid; i < pl.T * 64; i += kSlideThreads) {
-                const int wl = i >> 6, e = i & 63;
-                double v = -2.0;
-                if (wl < nvalid && e < band) { const double2 x = top.xb[wl * band + e]; v = x.x * x.x + x.y * x.y; }
-                pwa[i] = v;
-            }
-        } else {
+        const int pws = lay.Lg == 8 ? 64 : band;
+        if (lay.Lg != 8) {
+            // run-time group width: powers in shared memory for the K scan rounds (the 8-lane
+            // network of the common case reads the captured bins directly)
             for (int i = tid; i < nvalid * band; i += kSlideThreads) { double2 v = top.xb[i]; pwa[i] = v.x * v.x + v.y * v.y; }
+            __syncthreads();
         }
-        __syncthreads();
         const int wpb = 32 / lay.Lg;
         double* stage = reinterpret_cast<double*>(ov + ((pl.T * pws * 8 + 15) & ~15)) + warp * 512;
         for (int b0 = warp * wpb; b0 < nvalid; b0 += (kSlideThreads / 32) * wpb) {
             const int nb = (nvalid - b0) < wpb ? (nvalid - b0) : wpb;
             if (lay.Lg == 8)
-                warp_select_emit_batch<8>(p, pwa + b0 * 64, top.xb + b0 * band, band, lo, 8, nb, gw_tile + b0, stage);
+                warp_select_emit_batch<8>(p, nullptr, top.xb + b0 * band, band, lo, 8, nb, gw_tile + b0, stage);
             else
                 warp_select_emit_batch<0>(p, pwa + b0 * band, top.xb + b0 * band, band, lo, lay.Lg, nb, gw_tile + b0, stage);
         }
