@@ -61,4 +61,16 @@ __device__ __forceinline__ bool better(double p, int pos, double bp, int bpos) {
     return (p > bp) || (p == bp && pos < bpos);
 }
 
+// Host side: true the first time a kernel instantiation is launched on the current device (the
+// opt-in dynamic shared-memory size is a per-device function attribute).  `seen` is the caller's
+// static bit mask; a lost update only repeats a harmless cudaFuncSetAttribute.
+inline bool first_launch_on_device(unsigned long long& seen) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (seen & bit) return false;
+    seen |= bit;
+    return true;
+}
+
 }  // namespace ws

@@ -60,12 +60,11 @@ cudaError_t launch_inverse_real(const double* d_spec, int32_t N, int32_t n_windo
     int log2N = 0;
     while ((1 << log2N) < N) log2N++;
     size_t smem = (size_t)N * 16;   // two buffers of N/2 double2
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_seen = 0;
+    if (first_launch_on_device(attr_seen)) {
         cudaError_t e = cudaFuncSetAttribute(inverse_real_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     if (smem > 232448) return cudaErrorInvalidValue;
     inverse_real_kernel<<<n_windows, 128, smem, stream>>>(d_spec, N, log2N, tw, d_out);

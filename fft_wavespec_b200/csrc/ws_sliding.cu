@@ -45,6 +45,8 @@ struct SlideLayout {
     int band;           // captured bins per window
     int epi_mode;        // 2: batched warp epilogue (insertion rule); 0: warp-per-window path (sort rule)
     int Lg;             // lanes per window of the batched warp epilogue
+    int overlap;        // 1: producer/consumer kernel (selection runs beside the top pass)
+    int stage_off;      // overlap: consumer warps' row staging (outside the live work area)
     int total_bytes;
 };
 
@@ -188,13 +190,105 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     (void)lane;
 }
 
+// ---- producer / consumer form of the fused kernel -------------------------------------------------
+// Measured on B200: two warps per CTA already keep the HBM store stream of the top pass saturated,
+// while the selection + row arithmetic is latency bound.  So when a tile's chains fit four warps
+// (S (Q - 1) <= 128) the CTA splits after the lower passes: the first ceil(S (Q - 1) / 32) warps run
+// the chains and stream the spectra; the other warps first emit the packed-slot bins, then pick up
+// each group of four windows as soon as the chains have produced it (named barriers 1 + it:
+// producers arrive, the consumer warps that own a group of iteration `it` wait) and run the top-K
+// network and the row stores beside the producers.  Nothing is waited for by the producers, and the band capture needs no double
+// buffering because a group's rows are only written before its barrier.
+__device__ __forceinline__ void named_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+template <int N, bool SPEC>
+__global__ void __launch_bounds__(kSlideThreads, 2)
+sliding_overlap_kernel(const Params p, const Plan pl, const SlideLayout lay) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* x = reinterpret_cast<double*>(smem_raw);
+    double2* arena = reinterpret_cast<double2*>(smem_raw + lay.arena_off);
+    const int tid = threadIdx.x;
+    const int s = blockIdx.y;
+    const int64_t w0 = p.win_offset + (int64_t)blockIdx.x * pl.T;
+    const int64_t wend = p.win_offset + p.chunk_nwin;
+    const double* src = p.series + (int64_t)s * p.series_stride;
+    const int nvalid = (int)((wend - w0) < pl.T ? (wend - w0) : pl.T);
+
+    for (int i = tid; i < pl.x_len; i += kSlideThreads) {
+        int64_t a = w0 + i;
+        x[i] = (a < p.series_len) ? src[a] : 0.0;
+    }
+    __syncthreads();
+    ws_slide::bottom_level(tid, kSlideThreads, x, pl, p.tw, arena);
+    __syncthreads();
+    for (int i = pl.nst; i >= 2; i--) {
+        ws_slide::SmemSink sink{arena + pl.off[i - 1], pl.stride[i - 1]};
+        ws_slide::direct_pass(tid, kSlideThreads, arena + pl.off[i], pl.stride[i], pl.Q[i], 1 << pl.lev[i - 1],
+                              pl.P[i - 1], p.tw, pl.N, pl.lev[i - 1], sink);
+        __syncthreads();
+    }
+
+    TopSink<N, SPEC, 1, 3> top;
+    top.g = SPEC ? reinterpret_cast<double2*>(p.spectra) + ((int64_t)s * p.nwin + w0) * (N / 2) : nullptr;
+    top.xb = reinterpret_cast<double2*>(smem_raw + lay.xb_off);
+    top.lo = p.band_lo; top.hi = p.band_hi; top.band = lay.band;
+    top.nvalid = nvalid;
+    constexpr int gen = ws_slide::TopGeom<N>::Q - 1;
+    const int per = pl.T / pl.S;                 // windows per chain, a multiple of 4
+    const int iters = per >> 2;
+    const int nprod = ((pl.S * gen + 31) >> 5) << 5;          // producer threads: whole warps
+    const int bar_count = nprod + pl.S * 32;     // an iteration is awaited by one consumer warp per segment
+    const double2* lvl3 = arena + pl.off[1];
+
+    if (tid < nprod) {
+        const bool active = tid < pl.S * gen;
+        const int sub = active ? tid / gen : 0;
+        const int k = active ? 1 + tid - sub * gen : 1;
+        ws_slide::chain_single<N>(active, k, sub * per, per, lvl3, p.tw, top, [&](int it) {
+            __threadfence_block();               // the group's captured bins before the arrival
+            __syncwarp();
+            named_arrive(1 + it, bar_count);
+        });
+        return;
+    }
+
+    // consumers: packed-slot bins of all windows first (they may lie inside the band)
+    const int ncons = kSlideThreads - nprod;
+    const int ctid = tid - nprod;
+    const int cw = ctid >> 5, ncw = ncons >> 5;
+    ws_slide::special_pass<N>(ctid, ncons, lvl3, pl.T, p.tw, top);
+    named_sync(15, ncons);
+    const int64_t gw_tile = (int64_t)s * p.nwin + w0;
+    double* stage = reinterpret_cast<double*>(smem_raw + lay.stage_off) + cw * 512;
+    // groups of four windows in completion order: b = it * S + segment; consumer warp cw takes
+    // b = cw, cw + ncw, ...  (S <= ncw, so a warp waits on an iteration's barrier at most once)
+    for (int b = cw; b < iters * pl.S; b += ncw) {
+        const int it = b / pl.S, seg = b - it * pl.S;
+        named_sync(1 + it, bar_count);
+        const int b0 = seg * per + 4 * it;
+        if (b0 < nvalid) {
+            const int nb = (nvalid - b0) < 4 ? (nvalid - b0) : 4;
+            warp_select_emit_batch<8>(p, nullptr, top.xb + b0 * lay.band, lay.band, top.lo, 8, nb, gw_tile + b0, stage);
+        }
+    }
+}
+
 static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
+    // Tile shapes measured on B200 (profiles/README.md).  With selection outputs the chains of a
+    // tile are kept on four warps (S (N/16 - 1) <= 128) so that the producer / consumer kernel
+    // can run the selection beside them; a pure spectra writer is HBM bound with any S.
+    const bool any_sel = (p.bins || p.rows || p.waves || p.contrib) && !p.band_buf;
     int T, S;
     switch (p.N) {
         case 256:  T = 128; S = 16; break;
-        case 512:  T = 64;  S = 8;  break;
-        case 1024: T = 32;  S = 4;  break;
-        case 2048: T = 16;  S = 2;  break;
+        case 512:  T = 64;  S = any_sel ? 4 : 8; break;
+        case 1024: T = 32;  S = any_sel ? 2 : 1; break;
+        case 2048: T = 16;  S = any_sel ? 1 : 2; break;
         case 4096: T = 16;  S = 1;  break;
         default: return false;
     }
@@ -249,6 +343,31 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
         end = ov_bytes + xb_bytes;
     }
     if (!sel || lay.band == 0) end = 0;
+    // producer / consumer form: insertion rule with the 8-lane network, chains on four warps, one
+    // consumer warp per segment (S divides the four consumer warps), at most 14 iterations
+    // (named barriers 1..14)
+    lay.overlap = 0;
+    lay.stage_off = 0;
+    {
+        const int gen = (p.N >> 4) - 1;
+        const int per = pl.T / pl.S;
+        static int want = -1;
+        if (want < 0) { const char* e = getenv("WAVESPEC_OVERLAP"); want = (e && e[0] == '0') ? 0 : 1; }
+        if (want && sel && lay.band > 0 && lay.epi_mode == 2 && lay.Lg == 8 && pl.top == 3 && p.N <= 2048 &&
+            p.spectra && pl.S * gen <= 128 && pl.S <= (kSlideThreads - ((pl.S * gen + 31) & ~31)) / 32 &&
+            per % 4 == 0 && per / 4 <= 14) {
+            // capture and row staging live beside the work area (level 3 is read throughout)
+            const int xo = (work_end + 15) & ~15;
+            const int so = (xo + xb_bytes + 15) & ~15;
+            const int stage_bytes = (kSlideThreads - ((pl.S * gen + 31) & ~31)) / 32 * 512 * 8;   // per consumer warp
+            if (so + stage_bytes <= 113 * 1024) {        // keep two CTAs per SM
+                lay.overlap = 1;
+                lay.xb_off = xo;
+                lay.stage_off = so;
+                end = so + stage_bytes;
+            }
+        }
+    }
     lay.total_bytes = end > work_end ? end : work_end;
     lay.total_bytes = (lay.total_bytes + 15) & ~15;
     return lay.total_bytes <= 232448;
@@ -262,15 +381,28 @@ bool sliding_shared_supported(const Params& p) {
 
 template <int N, bool SPEC, int CAP, int TOP>
 static cudaError_t launch_top(const Params& p, const Plan& pl, const SlideLayout& lay, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_seen = 0;
+    if (first_launch_on_device(attr_seen)) {
         cudaError_t e = cudaFuncSetAttribute(sliding_shared_kernel<N, SPEC, CAP, TOP>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     dim3 grid((unsigned)((p.chunk_nwin + pl.T - 1) / pl.T), (unsigned)p.n_series);
     sliding_shared_kernel<N, SPEC, CAP, TOP><<<grid, kSlideThreads, lay.total_bytes, stream>>>(p, pl, lay);
+    return cudaGetLastError();
+}
+
+template <int N, bool SPEC>
+static cudaError_t launch_overlap(const Params& p, const Plan& pl, const SlideLayout& lay, cudaStream_t stream) {
+    if (N > 2048) return cudaErrorInvalidValue;          // chains of N = 4096 need all eight warps
+    static unsigned long long attr_seen = 0;
+    if (first_launch_on_device(attr_seen)) {
+        cudaError_t e = cudaFuncSetAttribute(sliding_overlap_kernel<N, SPEC>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid((unsigned)((p.chunk_nwin + pl.T - 1) / pl.T), (unsigned)p.n_series);
+    sliding_overlap_kernel<N, SPEC><<<grid, kSlideThreads, lay.total_bytes, stream>>>(p, pl, lay);
     return cudaGetLastError();
 }
 
@@ -287,6 +419,7 @@ static cudaError_t launch_n(const Params& p, const Plan& pl, const SlideLayout& 
         if (spec) return launch_one<N, true, 2>(p, pl, lay, stream);
         return launch_one<N, false, 2>(p, pl, lay, stream);
     }
+    if (sel && lay.overlap) return spec ? launch_overlap<N, true>(p, pl, lay, stream) : launch_overlap<N, false>(p, pl, lay, stream);
     if (spec && sel) return launch_one<N, true, 1>(p, pl, lay, stream);
     if (spec) return launch_one<N, true, 0>(p, pl, lay, stream);
     if (sel) return launch_one<N, false, 1>(p, pl, lay, stream);

@@ -294,43 +294,53 @@ WS_HD void chain_step(const double2*& nxt, double2& qold, double2& f2oP, double2
     bfly_alt(f1[3], g[3], w0c, P, R); sink.template put<6>(P); sink.template put<7>(R);   // W^{2Q+k}
 }
 
-template <int N, class Sink>
-WS_HD void chain_pass(int tid, int nthreads, const double2* in, int T, int S, const double2* tw, Sink& sink) {
+// One chain: slot k of level 3, windows m0 .. m0 + per - 1 (per a multiple of 4).  HOOK(it) runs
+// after every unrolled group of four windows — also for threads with active == false, which skip
+// the arithmetic but keep the control flow of their warp uniform (the overlapped kernel arrives on
+// a named barrier there).
+template <int N, class Sink, class Hook>
+WS_HD void chain_single(bool active, int k, int m0, int per, const double2* in, const double2* tw, Sink& sink,
+                        Hook hook) {
     constexpr int Q = TopGeom<N>::Q;
     constexpr int stride = TopGeom<N>::stride;
-    constexpr int gen = Q - 1;
-    const int per = T / S;                       // multiple of 4 (plan_make)
-    for (int c = tid; c < S * gen; c += nthreads) {
-        const int sub = c / gen, k = 1 + c - sub * gen;
-        const double2 w2 = tw[4 * k];            // W_{N/4}^k (level 2 has DFT length N/4)
-        const double2 w1a = tw[2 * k];           // W_{N/2}^k
-        const double2 w0a = tw[k];               // W_N^k
-        const double2 w0c = tw[2 * Q - k];       // W_N^{2Q-k}
-        const double2* src = in + k;
-        const int m0 = sub * per;
-        sink.bind(k);
-        double2 qa, qb, qc, qd;                  // inputs I_{m+3..m+6}
-        double2 eP, eR, oP, oR;                  // F2(m+1), F2(m+2)
-        double2 ha[4], hb[4];                    // F1(m) / F1(m+1), alternating
-        {
-            const double2 I0 = src[m0 * stride], I1 = src[(m0 + 1) * stride], I2 = src[(m0 + 2) * stride];
-            qa = src[(m0 + 3) * stride]; qb = src[(m0 + 4) * stride];
-            qc = src[(m0 + 5) * stride]; qd = src[(m0 + 6) * stride];
-            double2 zP, zR;
-            bfly(I0, qb, w2, zP, zR);            // F2(m0)
-            bfly(I1, qc, w2, eP, eR);            // F2(m0+1)
-            bfly(I2, qd, w2, oP, oR);            // F2(m0+2)
-            bfly(zP, oP, w1a, ha[0], ha[1]);     // F1(m0)
-            bfly_alt(zR, oR, w1a, ha[2], ha[3]);
-        }
-        const double2* nxt = src + (m0 + 7) * stride;
-        for (int m = m0; m < m0 + per; m += 4) {
+    const double2 w2 = tw[4 * k];            // W_{N/4}^k (level 2 has DFT length N/4)
+    const double2 w1a = tw[2 * k];           // W_{N/2}^k
+    const double2 w0a = tw[k];               // W_N^k
+    const double2 w0c = tw[2 * Q - k];       // W_N^{2Q-k}
+    const double2* src = in + k;
+    sink.bind(k);
+    double2 qa, qb, qc, qd;                  // inputs I_{m+3..m+6}
+    double2 eP, eR, oP, oR;                  // F2(m+1), F2(m+2)
+    double2 ha[4], hb[4];                    // F1(m) / F1(m+1), alternating
+    {
+        const double2 I0 = src[m0 * stride], I1 = src[(m0 + 1) * stride], I2 = src[(m0 + 2) * stride];
+        qa = src[(m0 + 3) * stride]; qb = src[(m0 + 4) * stride];
+        qc = src[(m0 + 5) * stride]; qd = src[(m0 + 6) * stride];
+        double2 zP, zR;
+        bfly(I0, qb, w2, zP, zR);            // F2(m0)
+        bfly(I1, qc, w2, eP, eR);            // F2(m0+1)
+        bfly(I2, qd, w2, oP, oR);            // F2(m0+2)
+        bfly(zP, oP, w1a, ha[0], ha[1]);     // F1(m0)
+        bfly_alt(zR, oR, w1a, ha[2], ha[3]);
+    }
+    const double2* nxt = src + (m0 + 7) * stride;
+    int it = 0;
+    for (int m = m0; m < m0 + per; m += 4, it++) {
+        if (active) {
             chain_step<N>(nxt, qa, eP, eR, ha, hb, w2, w1a, w0a, w0c, m, sink);
             chain_step<N>(nxt, qb, oP, oR, hb, ha, w2, w1a, w0a, w0c, m + 1, sink);
             chain_step<N>(nxt, qc, eP, eR, ha, hb, w2, w1a, w0a, w0c, m + 2, sink);
             chain_step<N>(nxt, qd, oP, oR, hb, ha, w2, w1a, w0a, w0c, m + 3, sink);
         }
+        hook(it);
     }
+}
+
+// bins that come from the packed slot 0 of level 3 (multiples of Q): one window per thread
+template <int N, class Sink>
+WS_HD void special_pass(int tid, int nthreads, const double2* in, int T, const double2* tw, Sink& sink) {
+    constexpr int Q = TopGeom<N>::Q;
+    constexpr int stride = TopGeom<N>::stride;
     const Tw4s ts = load_tw4s(tw, N, N, Q);
     for (int m = tid; m < T; m += nthreads) {
         double2 I[8], o[8];
@@ -340,6 +350,17 @@ WS_HD void chain_pass(int tid, int nthreads, const double2* in, int T, int S, co
         slot_index8_special(Q, idx);
         for (int j = 0; j < 8; j++) sink.put0(m, idx[j], o[j]);
     }
+}
+
+template <int N, class Sink>
+WS_HD void chain_pass(int tid, int nthreads, const double2* in, int T, int S, const double2* tw, Sink& sink) {
+    constexpr int gen = TopGeom<N>::Q - 1;
+    const int per = T / S;                       // multiple of 4 (plan_make)
+    for (int c = tid; c < S * gen; c += nthreads) {
+        const int sub = c / gen, k = 1 + c - sub * gen;
+        chain_single<N>(true, k, sub * per, per, in, tw, sink, [](int) {});
+    }
+    special_pass<N>(tid, nthreads, in, T, tw, sink);
 }
 
 // ---- radix-4 top pass (levels 2 -> 0): half the register state of the radix-8 chain -------------

@@ -344,11 +344,10 @@ template <int NT, int LN, int CAP>
 static cudaError_t launch_nt(Params p, cudaStream_t stream) {
     p.tile_windows = window_fft_pick_tile(p, NT);
     size_t smem = window_fft_smem_bytes(p, p.tile_windows, NT);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_seen = 0;
+    if (first_launch_on_device(attr_seen)) {
         cudaError_t e = cudaFuncSetAttribute(window_fft_kernel<NT, LN, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     if (smem > 232448) return cudaErrorInvalidValue;
     dim3 grid((unsigned)((p.chunk_nwin + p.tile_windows - 1) / p.tile_windows), (unsigned)p.n_series);
