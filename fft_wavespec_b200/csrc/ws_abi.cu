@@ -389,10 +389,11 @@ int run_pipeline(const double* d_series, int32_t n_series, int32_t series_len,
                     }
                     g_launches--;      // the common increment below counts one of them
                     if (rc2) return rc2;
+                    g_last_kernel = "sliding_shared";
                 } else {
-                    WS_CUDA(ws::launch_sliding_shared(p, st), "sliding_shared kernel");
+                    g_last_kernel = "sliding_shared";
+                    WS_CUDA(ws::launch_sliding_shared(p, st, &g_last_kernel), "sliding_shared kernel");
                 }
-                g_last_kernel = "sliding_shared";
             } else {
                 WS_CUDA(ws::launch_window_fft(p, st, &g_last_kernel), "window_fft kernel");
             }

@@ -43,7 +43,8 @@ cudaError_t launch_window_fft_warp(Params p, cudaStream_t stream);
 
 // ws_sliding.cu
 bool sliding_shared_supported(const Params& p);
-cudaError_t launch_sliding_shared(Params p, cudaStream_t stream);
+// *which (when non-null) receives "sliding_overlap" if the producer / consumer form ran
+cudaError_t launch_sliding_shared(Params p, cudaStream_t stream, const char** which = nullptr);
 
 // ws_rows.cu
 bool rows_from_band_supported(const Params& p);

@@ -279,16 +279,17 @@ sliding_overlap_kernel(const Params p, const Plan pl, const SlideLayout lay) {
 }
 
 static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
-    // Tile shapes measured on B200 (profiles/README.md).  With selection outputs the chains of a
-    // tile are kept on four warps (S (N/16 - 1) <= 128) so that the producer / consumer kernel
-    // can run the selection beside them; a pure spectra writer is HBM bound with any S.
+    // Tile shapes measured on B200 (profiles/README.md).  With spectra AND selection outputs the
+    // chains of a tile are kept on four warps (S (N/16 - 1) <= 128) so that the producer /
+    // consumer kernel can run the selection beside them; a pure spectra writer is HBM bound with
+    // any S (fewest chains win), a pure row producer wants all eight warps on the chains.
     const bool any_sel = (p.bins || p.rows || p.waves || p.contrib) && !p.band_buf;
     int T, S;
     switch (p.N) {
         case 256:  T = 128; S = 16; break;
-        case 512:  T = 64;  S = any_sel ? 4 : 8; break;
-        case 1024: T = 32;  S = any_sel ? 2 : 1; break;
-        case 2048: T = 16;  S = any_sel ? 1 : 2; break;
+        case 512:  T = 64;  S = (any_sel && p.spectra) ? 4 : 8; break;
+        case 1024: T = 32;  S = any_sel ? (p.spectra ? 2 : 4) : 1; break;
+        case 2048: T = 16;  S = 2;  break;
         case 4096: T = 16;  S = 1;  break;
         default: return false;
     }
@@ -426,9 +427,10 @@ static cudaError_t launch_n(const Params& p, const Plan& pl, const SlideLayout& 
     return cudaSuccess;
 }
 
-cudaError_t launch_sliding_shared(Params p, cudaStream_t stream) {
+cudaError_t launch_sliding_shared(Params p, cudaStream_t stream, const char** which) {
     Plan pl; SlideLayout lay;
     if (!pick_plan(p, pl, lay)) return cudaErrorInvalidValue;
+    if (which && lay.overlap && !p.band_buf) *which = "sliding_overlap";
     p.tile_windows = pl.T;
     switch (p.N) {
         case 256: return launch_n<256>(p, pl, lay, stream);

@@ -234,7 +234,7 @@ def test_sliding_shared_kernel_all_lengths_and_ragged_tiles(br, oracle, n):
         cfg = br.default_cfg(n, top_k=8, min_period=9.0, max_period=200.0)
         out = br.OUT_SPECTRA | br.OUT_BINS | br.OUT_ROWS | br.OUT_WAVES
         got = br.pipeline_host(s, cfg, out)
-        assert br.last_kernel() in ("sliding_shared", "sliding_ws")
+        assert br.last_kernel() in ("sliding_shared", "sliding_overlap")
         for i in range(2):
             ref = oracle.pipeline_series(s[i], ocfg_from(oracle, cfg), out)
             check_planes(br, {k: v[i] for k, v in got.items()}, ref, cfg)
@@ -248,7 +248,7 @@ def test_sliding_shared_rows_only_and_sort_rule(br, oracle):
         cfg = br.default_cfg(1024, top_k=8, min_period=12.0, max_period=256.0, select=sel)
         out = br.OUT_BINS | br.OUT_ROWS | br.OUT_WKALMAN
         got, ref = run_both(br, oracle, s, cfg, out)
-        assert br.last_kernel() in ("sliding_shared", "sliding_ws")
+        assert br.last_kernel() in ("sliding_shared", "sliding_overlap")
         check_planes(br, got, ref, cfg)
 
 
@@ -259,7 +259,7 @@ def test_sliding_shared_long_series_spot_checks(br, oracle):
     s = synth.random_walk(220, 200000)
     cfg = br.default_cfg(n, top_k=8, outputs=br.OUT_BINS | br.OUT_SPECTRA)
     got = br.pipeline_host(s, cfg)
-    assert br.last_kernel() in ("sliding_shared", "sliding_ws")
+    assert br.last_kernel() in ("sliding_shared", "sliding_overlap")
     nw = got["bins"].shape[0]
     ocfg = ocfg_from(oracle, cfg)
     for w0 in (0, 31, 32, 12345, nw - 40):
