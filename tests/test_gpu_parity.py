@@ -706,3 +706,26 @@ def test_warp_kernel_many_series_rows_only(br, oracle):
     for i in range(s.shape[0]):
         ref = oracle.pipeline_series(s[i], ocfg_from(oracle, cfg), br.OUT_ROWS | br.OUT_BINS)
         check_planes(br, {k: (v[i] if v is not None else None) for k, v in got.items()}, ref, cfg)
+
+
+# ---- producer / consumer sliding kernel vs the phase-ordered one --------------------------------
+@pytest.mark.parametrize("n", [512, 1024])
+def test_overlap_kernel_rows_bit_identical_to_phase_kernel_and_repeatable(br, n):
+    """Spectra + rows run the producer / consumer kernel (selection beside the chains, named
+    barriers); rows alone run the kernel whose epilogue follows a block barrier.  Same arithmetic,
+    different schedule: rows and bins must agree bit for bit over ~10^5 tiles' worth of hand-offs,
+    and a second run must reproduce the first (a lost hand-off would show up as a mismatch)."""
+    s = synth.random_walk_batch(1200 + n, 4, 120_000 + n)
+    cfg = br.default_cfg(n, top_k=8, min_period=18.0, max_period=200.0)
+    both = br.pipeline_host(s, cfg, br.OUT_SPECTRA | br.OUT_ROWS | br.OUT_BINS)
+    assert br.last_kernel() == "sliding_overlap"
+    rows_only = br.pipeline_host(s, cfg, br.OUT_ROWS | br.OUT_BINS)
+    assert br.last_kernel() == "sliding_shared"
+    assert np.array_equal(both["bins"], rows_only["bins"])
+    assert np.array_equal(both["rows"], rows_only["rows"])
+    again = br.pipeline_host(s, cfg, br.OUT_SPECTRA | br.OUT_ROWS | br.OUT_BINS)
+    assert np.array_equal(both["bins"], again["bins"])
+    assert np.array_equal(both["rows"], again["rows"])
+    assert np.array_equal(both["spectra"], again["spectra"])
+    spec_only = br.pipeline_host(s, cfg, br.OUT_SPECTRA)
+    assert np.array_equal(both["spectra"], spec_only["spectra"])
