@@ -100,6 +100,10 @@ def lib():
     L.wavespec_pla_windows_host.restype = i32
     L.wavespec_zigzag_feed_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, dbl, i32, vp, vp]
     L.wavespec_zigzag_feed_host.restype = i32
+    L.wavespec_applied_price_host.argtypes = [vp, vp, vp, vp, C.c_int64, i32, vp]
+    L.wavespec_applied_price_host.restype = i32
+    L.wavespec_applied_price_device.argtypes = [vp, vp, vp, vp, C.c_int64, i32, vp, vp]
+    L.wavespec_applied_price_device.restype = i32
     L.wavespec_cycle_cache_host.argtypes = [vp, i32, i32, i32, i32, i32, i32, dbl, C.POINTER(CacheParams), vp]
     L.wavespec_cycle_cache_host.restype = i32
     L.wavespec_launch_count.argtypes = []; L.wavespec_launch_count.restype = i64
@@ -115,7 +119,8 @@ EXPORTED_SYMBOLS = [
     "gpu_get_last_error_w", "gpu_fft_real_inverse", "gpu_fft_real_forward_batch",
     "wavespec_default_cfg", "wavespec_num_windows", "wavespec_pipeline_host", "wavespec_pipeline_device",
     "wavespec_fft_real_forward_sliding", "wavespec_pla_windows_host", "wavespec_zigzag_feed_host",
-    "wavespec_cycle_cache_host", "wavespec_launch_count",
+    "wavespec_cycle_cache_host", "wavespec_applied_price_host", "wavespec_applied_price_device",
+    "wavespec_launch_count",
     "wavespec_last_kernel", "wavespec_version",
 ]
 
@@ -292,6 +297,21 @@ def zigzag_feed_host(zz_main, zz_high, zz_low, window_len, hop=1, pivot_rule=0, 
     _check(lib().wavespec_zigzag_feed_host(_ptr(m), _ptr(h), _ptr(lo), m.size, window_len, hop, pivot_rule, mode,
                                            float(fallback), min_pivots, _ptr(lines), _ptr(valid)))
     return lines, valid
+
+
+PRICE_CLOSE, PRICE_OPEN, PRICE_HIGH, PRICE_LOW, PRICE_MEDIAN, PRICE_TYPICAL, PRICE_WEIGHTED = range(1, 8)
+
+
+def applied_price_host(open_, high, low, close, mode):
+    """A1: per-bar applied price series (mode = MQL5 ENUM_APPLIED_PRICE value); unused inputs may be None."""
+    arrs = [None if a is None else _f64(a) for a in (open_, high, low, close)]
+    sizes = {a.size for a in arrs if a is not None}
+    if len(sizes) != 1:
+        raise ValueError("price series must be present and equally long")
+    n = sizes.pop()
+    out = np.empty(n)
+    _check(lib().wavespec_applied_price_host(*[_ptr(a) for a in arrs], n, int(mode), _ptr(out)))
+    return out
 
 
 def cycle_cache_host(rows, top_k, window_len, hop, bars, period_seconds=60.0, music_only=False,

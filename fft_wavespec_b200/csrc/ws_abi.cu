@@ -930,6 +930,56 @@ int32_t wavespec_zigzag_feed_host(const double* zz_main, const double* zz_high, 
     return WAVESPEC_OK;
 }
 
+static int applied_price_args(const double* o, const double* h, const double* l, const double* c, int64_t n,
+                              int32_t mode, const double* out) {
+    if (n < 1 || !out) return fail(WAVESPEC_BAD_ARGS, "n_bars must be >= 1 and out non-null");
+    if (mode < WAVESPEC_PRICE_CLOSE || mode > WAVESPEC_PRICE_WEIGHTED) return fail(WAVESPEC_BAD_ARGS, "bad applied-price mode");
+    const bool need_o = mode == WAVESPEC_PRICE_OPEN;
+    const bool need_c = mode == WAVESPEC_PRICE_CLOSE || mode >= WAVESPEC_PRICE_TYPICAL;
+    const bool need_h = mode == WAVESPEC_PRICE_HIGH || mode >= WAVESPEC_PRICE_MEDIAN;
+    const bool need_l = mode == WAVESPEC_PRICE_LOW || mode >= WAVESPEC_PRICE_MEDIAN;
+    if ((need_o && !o) || (need_c && !c) || (need_h && !h) || (need_l && !l))
+        return fail(WAVESPEC_BAD_ARGS, "a price series this mode reads is null");
+    return WAVESPEC_OK;
+}
+
+int32_t wavespec_applied_price_device(const double* d_open, const double* d_high, const double* d_low,
+                                      const double* d_close, int64_t n_bars, int32_t mode, double* d_out,
+                                      void* stream) {
+    int rc = ensure_open();
+    if (rc) return rc;
+    if ((rc = applied_price_args(d_open, d_high, d_low, d_close, n_bars, mode, d_out))) return rc;
+    WS_CUDA(ws::launch_applied_price(d_open, d_high, d_low, d_close, n_bars, mode, d_out,
+                                     static_cast<cudaStream_t>(stream)), "applied_price kernel");
+    g_launches++;
+    g_last_kernel = "applied_price";
+    return WAVESPEC_OK;
+}
+
+int32_t wavespec_applied_price_host(const double* open, const double* high, const double* low, const double* close,
+                                    int64_t n_bars, int32_t mode, double* out) {
+    int rc = ensure_open();
+    if (rc) return rc;
+    if ((rc = applied_price_args(open, high, low, close, n_bars, mode, out))) return rc;
+    const size_t sb = (size_t)n_bars * 8;
+    DeviceBuf dbuf[4], dout;
+    const double* hsrc[4] = {open, high, low, close};
+    cudaStream_t st = pick_stream();
+    WS_CUDA(dout.alloc(sb), "cudaMalloc(applied price)");
+    for (int i = 0; i < 4; i++) {
+        if (!hsrc[i]) continue;
+        WS_CUDA(dbuf[i].alloc(sb), "cudaMalloc(price series)");
+        WS_CUDA(cudaMemcpyAsync(dbuf[i].p, hsrc[i], sb, cudaMemcpyHostToDevice, st), "H2D price series");
+    }
+    WS_CUDA(ws::launch_applied_price(dbuf[0].as<double>(), dbuf[1].as<double>(), dbuf[2].as<double>(),
+                                     dbuf[3].as<double>(), n_bars, mode, dout.as<double>(), st), "applied_price kernel");
+    g_launches++;
+    g_last_kernel = "applied_price";
+    WS_CUDA(cudaMemcpyAsync(out, dout.p, sb, cudaMemcpyDeviceToHost, st), "D2H applied price");
+    WS_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    return WAVESPEC_OK;
+}
+
 int32_t wavespec_cycle_cache_host(const double* rows, int32_t n_windows, int32_t top_k, int32_t stride,
                                   int32_t window_len, int32_t hop, int32_t bars, double period_seconds,
                                   const wavespec_cache_params* params, double* out) {

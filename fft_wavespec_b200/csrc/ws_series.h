@@ -65,6 +65,8 @@ cudaError_t launch_pla(const double* series, int64_t series_stride, int32_t n_se
                        cudaStream_t stream);
 
 // ws_zigzag.cu
+cudaError_t launch_applied_price(const double* o, const double* h, const double* l, const double* c, int64_t n,
+                                 int mode, double* out, cudaStream_t stream);
 cudaError_t launch_zigzag(const double* zmain, const double* zhigh, const double* zlow, const double* fallback,
                           int32_t n_series, int32_t len, int32_t N, int32_t hop, int rule, int mode, int min_pivots,
                           double* pv, int32_t* prev, int32_t* next, double* lines, int32_t* valid,

@@ -102,4 +102,34 @@ cudaError_t launch_zigzag(const double* zmain, const double* zhigh, const double
     return cudaGetLastError();
 }
 
+// ---- applied price (A1): Legacy/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:3308-3316 --------------------
+// One bar per thread, grid-stride; this file is compiled with -fmad=false, and the expressions
+// keep the reference's operand order, so the series is bit-identical to the MQL5 loop.
+__global__ void applied_price_kernel(const double* __restrict__ o, const double* __restrict__ h,
+                                     const double* __restrict__ l, const double* __restrict__ c, int64_t n,
+                                     int mode, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v;
+        switch (mode) {
+            case 1: v = c[i]; break;
+            case 2: v = o[i]; break;
+            case 3: v = h[i]; break;
+            case 4: v = l[i]; break;
+            case 5: v = (h[i] + l[i]) / 2.0; break;
+            case 6: v = (h[i] + l[i] + c[i]) / 3.0; break;
+            default: v = (h[i] + l[i] + 2 * c[i]) / 4.0; break;
+        }
+        out[i] = v;
+    }
+}
+
+cudaError_t launch_applied_price(const double* o, const double* h, const double* l, const double* c, int64_t n,
+                                 int mode, double* out, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    applied_price_kernel<<<(unsigned)blocks, 256, 0, stream>>>(o, h, l, c, n, mode, out);
+    return cudaGetLastError();
+}
+
 }  // namespace ws

@@ -226,6 +226,22 @@ WAVESPEC_API int32_t wavespec_pla_windows_host(const double* series, int32_t ser
                                                double* lines, int32_t* seg_bounds,
                                                int32_t* seg_counts);
 
+/* Applied-price series (A1): the per-bar series the windows are cut from, for the price sources of
+ * Legacy/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:3308-3316 (FFT_APPLIED_PRICE_SOURCE, :807-818, values
+ * of MQL5's ENUM_APPLIED_PRICE): close, open, high, low, median (high+low)/2, typical
+ * (high+low+close)/3, weighted (high+low+2*close)/4 — evaluated per bar in the reference's operand
+ * order, bit-identical to the MQL5 loop.  Unused inputs of a mode may be NULL. */
+enum {
+    WAVESPEC_PRICE_CLOSE = 1, WAVESPEC_PRICE_OPEN = 2, WAVESPEC_PRICE_HIGH = 3, WAVESPEC_PRICE_LOW = 4,
+    WAVESPEC_PRICE_MEDIAN = 5, WAVESPEC_PRICE_TYPICAL = 6, WAVESPEC_PRICE_WEIGHTED = 7
+};
+WAVESPEC_API int32_t wavespec_applied_price_host(const double* open, const double* high, const double* low,
+                                                 const double* close, int64_t n_bars, int32_t mode, double* out);
+/* same on device pointers, asynchronous on `stream` (a cudaStream_t, NULL = default stream) */
+WAVESPEC_API int32_t wavespec_applied_price_device(const double* d_open, const double* d_high, const double* d_low,
+                                                   const double* d_close, int64_t n_bars, int32_t mode,
+                                                   double* d_out, void* stream);
+
 /* ZigZag pivot -> feed expansion of every window of one host series (A12).  zz_main / zz_high /
  * zz_low are the per-bar indicator buffers in chronological order (for 1.1.0, `main` is the
  * channel LoadWindow builds: buffer 0 where non-zero, else buffer 1 — WaveSpecZZ_1.1.0-gpuopt.mq5:

@@ -88,6 +88,8 @@ def lib():
     L.oracle_zigzag_feed_110.argtypes = [_dp, _dp, _dp, C.c_int, C.c_int, C.c_double, C.c_double, _dp]
     L.oracle_zigzag_series_legacy.argtypes = [_dp, _dp, _dp, C.c_int, C.c_int, _dp]
     L.oracle_zigzag_series_legacy.restype = C.c_int
+    L.oracle_applied_price.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, _dp]
+    L.oracle_applied_price.restype = C.c_int
     L.oracle_tracker_reset.argtypes = [C.POINTER(TrackerState)]
     L.oracle_tracker_step.argtypes = [C.POINTER(TrackerState), _dp, C.c_int, C.c_double, C.c_double, C.c_double,
                                       C.c_int, _ip, _dp]
@@ -199,6 +201,17 @@ def pla_build(window, max_segments=32, max_error=0.0005):
 def zigzag_feed_110(main_ch, high_ch, low_ch, mode, high0=0.0, low0=0.0):
     m = _f64(main_ch); out = np.empty_like(m)
     lib().oracle_zigzag_feed_110(m, _f64(high_ch), _f64(low_ch), m.size, int(mode), high0, low0, out)
+    return out
+
+
+def applied_price(open_, high, low, close, mode):
+    """A1: per-bar applied price (MQL5 ENUM_APPLIED_PRICE value as mode); unused series may be None."""
+    arrs = [None if a is None else _f64(a) for a in (open_, high, low, close)]
+    n = next(a.size for a in arrs if a is not None)
+    out = np.empty(n)
+    ptrs = [None if a is None else C.c_void_p(a.ctypes.data) for a in arrs]
+    if lib().oracle_applied_price(*ptrs, n, int(mode), out) != 0:
+        raise ValueError("unknown applied-price mode")
     return out
 
 

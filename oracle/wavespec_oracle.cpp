@@ -509,6 +509,25 @@ void oracle_zigzag_feed_110(const double* main_ch, const double* high_ch, const 
 }
 
 // A12 L/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:237-357 (current-timeframe branch)
+// Applied price, Legacy/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:3308-3316 (per-bar form of the
+// per-window loops: the value of bar start_pos + j does not depend on the window).
+int oracle_applied_price(const double* open, const double* high, const double* low, const double* close,
+                         long long n, int mode, double* out) {
+    for (long long j = 0; j < n; j++) {
+        switch (mode) {
+            case 1: out[j] = close[j]; break;                                         // :3310 ArrayCopy
+            case 2: out[j] = open[j]; break;                                          // :3311
+            case 3: out[j] = high[j]; break;                                          // :3312
+            case 4: out[j] = low[j]; break;                                           // :3313
+            case 5: out[j] = (high[j] + low[j]) / 2.0; break;                         // :3314
+            case 6: out[j] = (high[j] + low[j] + close[j]) / 3.0; break;              // :3315
+            case 7: out[j] = (high[j] + low[j] + 2 * close[j]) / 4.0; break;          // :3316
+            default: return -1;
+        }
+    }
+    return 0;
+}
+
 int oracle_zigzag_series_legacy(const double* zz_main, const double* zz_high, const double* zz_low,
                                 int n, int mode, double* price_data) {
     std::vector<int> pidx(n); std::vector<double> pval(n);

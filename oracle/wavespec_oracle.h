@@ -98,6 +98,12 @@ void oracle_zigzag_feed_110(const double* main_ch, const double* high_ch, const 
                             int len, int mode, double high0, double low0, double* feed);
 /* A12 L/...-kalman-fast.mq5:237-357 (current-timeframe branch); mode 0 CONTINUOUS, 1 ALTERNATING.
  * returns 0 when fewer than two pivots (the reference skips the bar). */
+/* Applied price (A1): Legacy/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:3308-3316; mode = MQL5
+ * ENUM_APPLIED_PRICE value (1 close, 2 open, 3 high, 4 low, 5 median, 6 typical, 7 weighted).
+ * Returns 0, or -1 for an unknown mode. */
+int oracle_applied_price(const double* open, const double* high, const double* low, const double* close,
+                         long long n, int mode, double* out);
+
 int oracle_zigzag_series_legacy(const double* zz_main, const double* zz_high, const double* zz_low,
                                 int n, int mode, double* price_data);
 

@@ -729,3 +729,38 @@ def test_overlap_kernel_rows_bit_identical_to_phase_kernel_and_repeatable(br, n)
     assert np.array_equal(both["spectra"], again["spectra"])
     spec_only = br.pipeline_host(s, cfg, br.OUT_SPECTRA)
     assert np.array_equal(both["spectra"], spec_only["spectra"])
+
+
+# ---- A1: applied price ---------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5, 6, 7])
+def test_applied_price_bit_exact(br, oracle, mode):
+    c = synth.random_walk(1300, 200_003)
+    h, l = synth.high_low(1300, c)
+    o = np.roll(c, 1); o[0] = c[0]
+    got = br.applied_price_host(o, h, l, c, mode)
+    assert br.last_kernel() == "applied_price"
+    assert np.array_equal(got, oracle.applied_price(o, h, l, c, mode))
+    # inputs a mode does not read may be omitted
+    need = {1: (0, 0, 0, 1), 2: (1, 0, 0, 0), 3: (0, 1, 0, 0), 4: (0, 0, 1, 0), 5: (0, 1, 1, 0),
+            6: (0, 1, 1, 1), 7: (0, 1, 1, 1)}[mode]
+    args = [a if k else None for a, k in zip((o, h, l, c), need)]
+    assert np.array_equal(br.applied_price_host(*args, mode), got)
+
+
+def test_applied_price_bad_args(br):
+    c = synth.random_walk(1301, 100)
+    for mode, args in ((0, (c, c, c, c)), (8, (c, c, c, c)), (6, (None, c, c, None)), (5, (None, None, c, None))):
+        with pytest.raises(br.WaveSpecError) as e:
+            br.applied_price_host(*args, mode)
+        assert e.value.status == br.BAD_ARGS
+
+
+def test_median_price_feeds_the_pipeline(br, oracle):
+    """The applied-price series is just another per-bar series for the window kernels."""
+    c = synth.random_walk(1302, 512 + 400)
+    h, l = synth.high_low(1302, c)
+    med = br.applied_price_host(None, h, l, None, br.PRICE_MEDIAN)
+    cfg = br.default_cfg(512, top_k=5, min_period=9.0, max_period=200.0, detrend=br.DETREND_MEAN,
+                         window_type=br.WINDOW_HANN_WIP)
+    got, ref = run_both(br, oracle, med, cfg, br.OUT_SPECTRA | br.OUT_BINS)
+    check_planes(br, got, ref, cfg)

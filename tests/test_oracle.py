@@ -368,3 +368,20 @@ def test_pipeline_batch_mt_equals_series_loop(oracle):
         r = oracle.pipeline_series(batch[i], cfg, oracle.OUT_BINS | oracle.OUT_SPECTRA)
         assert np.array_equal(out["bins"][i], r["bins"])
         assert np.array_equal(out["spectra"][i], r["spectra"])
+
+
+def test_applied_price_matches_the_reference_expressions(oracle):
+    """A1 (…-fast.mq5:3308-3316): operand order matters for the last bit — (h+l+c)/3, not h/3+l/3+c/3."""
+    c = synth.random_walk(77, 4000)
+    h, l = synth.high_low(77, c)
+    o = np.roll(c, 1); o[0] = c[0]
+    assert np.array_equal(oracle.applied_price(o, h, l, c, 1), c)
+    assert np.array_equal(oracle.applied_price(o, None, None, None, 2), o)
+    assert np.array_equal(oracle.applied_price(None, h, None, None, 3), h)
+    assert np.array_equal(oracle.applied_price(None, None, l, None, 4), l)
+    assert np.array_equal(oracle.applied_price(None, h, l, None, 5), (h + l) / 2.0)
+    assert np.array_equal(oracle.applied_price(None, h, l, c, 6), (h + l + c) / 3.0)
+    assert np.array_equal(oracle.applied_price(None, h, l, c, 7), (h + l + 2 * c) / 4.0)
+    assert not np.array_equal(oracle.applied_price(None, h, l, c, 6), h / 3.0 + l / 3.0 + c / 3.0)
+    with pytest.raises(ValueError):
+        oracle.applied_price(o, h, l, c, 9)
