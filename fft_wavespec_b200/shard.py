@@ -21,6 +21,27 @@ def strong_shard(total_series: int, rank: int, world: int):
     return range(first, first + count)
 
 
+def bar_range_shard(series_len: int, window_len: int, hop: int, rank: int, world: int):
+    """One series split over ranks by bar range (fewer series than GPUs, or one dominant series).
+
+    Returns (first_window, n_windows, first_sample, n_samples): rank `rank` owns the windows
+    [first_window, first_window + n_windows) of the series and must be handed the samples
+    [first_sample, first_sample + n_samples) — its windows plus a halo of window_len - hop samples
+    shared with the next rank.  Only the stateless stages (spectra, selection, rows, waves) may be
+    split this way; the per-series recursions (Kalman4D, weight-Kalman, tracker pool) stay on one
+    rank per series.  Ranks beyond the window count get n_windows = 0."""
+    if series_len < window_len:
+        return 0, 0, 0, 0
+    nwin = 1 + (series_len - window_len) // hop
+    base, rem = divmod(nwin, world)
+    w0 = rank * base + min(rank, rem)
+    cnt = base + (1 if rank < rem else 0)
+    if cnt == 0:
+        return w0, 0, 0, 0
+    a0 = w0 * hop
+    return w0, cnt, a0, (cnt - 1) * hop + window_len
+
+
 def max_over_ranks(value: float, device=None) -> float:
     import torch
     import torch.distributed as dist

@@ -764,3 +764,34 @@ def test_median_price_feeds_the_pipeline(br, oracle):
                          window_type=br.WINDOW_HANN_WIP)
     got, ref = run_both(br, oracle, med, cfg, br.OUT_SPECTRA | br.OUT_BINS)
     check_planes(br, got, ref, cfg)
+
+
+# ---- 8(e): one series split over GPUs by bar range ----------------------------------------------
+@pytest.mark.parametrize("n,plain", [(1024, True), (512, False)])
+def test_bar_range_split_reproduces_the_unsplit_series(br, n, plain):
+    """A rank that owns windows [w0, w0 + cnt) of a series gets the samples of those windows plus the
+    N - 1 halo; the stateless outputs of the pieces concatenate to the unsplit result.  Bitwise for
+    the plain sliding path (a window's butterfly tree does not depend on its tile); the tile-level
+    trend scan of the detrended path differs by rounding only."""
+    from fft_wavespec_b200 import shard
+    x = synth.random_walk(1400 + n, 50_000 + n)
+    if plain:
+        cfg = br.default_cfg(n, top_k=8, min_period=18.0, max_period=200.0)
+    else:
+        cfg = br.default_cfg(n, top_k=5, min_period=9.0, max_period=200.0, detrend=br.DETREND_IIR,
+                             trend_period=256.0, window_type=br.WINDOW_HANN)
+    outs = br.OUT_SPECTRA | br.OUT_ROWS | br.OUT_BINS
+    whole = br.pipeline_host(x, cfg, outs)
+    world = 3
+    parts = []
+    for r in range(world):
+        w0, cnt, a0, na = shard.bar_range_shard(x.size, n, 1, r, world)
+        parts.append(br.pipeline_host(x[a0:a0 + na], cfg, outs))
+        assert parts[-1]["bins"].shape[0] == cnt
+    for key in ("spectra", "rows", "bins"):
+        cat = np.concatenate([p[key] for p in parts])
+        if plain or key == "bins":
+            assert np.array_equal(cat, whole[key]), key
+        else:
+            scale = np.abs(whole[key]).max()
+            assert np.abs(cat - whole[key]).max() <= 1e-9 * scale, key
