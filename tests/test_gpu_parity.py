@@ -5,6 +5,8 @@ Bars (north_star): selected cycle bins and PLA pivot indices bit-exact; spectra 
 reconstructed waves within 1e-9 relative (max |dX| / max |X| per window)."""
 import ctypes as C
 
+import os
+
 import numpy as np
 import pytest
 
@@ -795,3 +797,48 @@ def test_bar_range_split_reproduces_the_unsplit_series(br, n, plain):
         else:
             scale = np.abs(whole[key]).max()
             assert np.abs(cat - whole[key]).max() <= 1e-9 * scale, key
+
+
+# ---- config 3 and config 1 at full length --------------------------------------------------------
+def test_config3_full_size_1m_bars_properties(br, oracle):
+    """One config-3 series at its full length (1M bars, N=2048, IIR T=1024 + Blackman, band 18-52):
+    the warp-per-window kernel over 997 953 windows.  Selected bins exact and waves within 1e-9 on a
+    strided sample of windows against the oracle (each window's trend filter restarts, so a window
+    is checked from its own 2048 samples); Kalman4D bit-identical over the whole series; the
+    selection is invariant under a power-of-two scale of the prices."""
+    n, bars = 2048, 1_000_000
+    s = synth.random_walk(8, bars)
+    cfg = br.default_cfg(n, top_k=8, min_period=18.0, max_period=52.0, detrend=br.DETREND_IIR,
+                         trend_period=1024.0, window_type=br.WINDOW_BLACKMAN)
+    got = br.pipeline_host(s, cfg, br.OUT_BINS | br.OUT_WAVES | br.OUT_KALMAN)
+    assert br.last_kernel() == "window_fft_warp"
+    nwin = bars - n + 1
+    assert got["bins"].shape == (nwin, 8)
+    assert got["bins"].min() >= 40 and got["bins"].max() <= 113          # SURVEY appendix A
+    ocfg = ocfg_from(oracle, cfg)
+    for w in list(range(0, nwin, 83_161)) + [nwin - 1]:
+        ref = oracle.pipeline_series(s[w:w + n], ocfg, oracle.OUT_BINS | oracle.OUT_WAVES)
+        assert np.array_equal(got["bins"][w], ref["bins"][0]), w
+        scale = np.abs(ref["waves"][0]).max()
+        assert np.abs(got["waves"][w] - ref["waves"][0]).max() <= REL_TOL * scale, w
+    refk = oracle.pipeline_series(s, ocfg, oracle.OUT_KALMAN)["kalman"]
+    assert np.array_equal(got["kalman"], refk)
+    got4 = br.pipeline_host(4.0 * s, cfg, br.OUT_BINS)
+    assert np.array_equal(got4["bins"], got["bins"])
+
+
+def test_config1_full_size_all_windows_against_oracle(br, oracle):
+    """Config 1 is small enough for the oracle to run every window: 100k bars, N=512, mean + Hann,
+    top-5, band 9-200 — all 99 489 windows, bins exact, spectra within 1e-9."""
+    n, bars = 512, 100_000
+    s = synth.random_walk(0, bars)
+    cfg = br.default_cfg(n, top_k=5, min_period=9.0, max_period=200.0, detrend=br.DETREND_MEAN,
+                         window_type=br.WINDOW_HANN_WIP)
+    got = br.pipeline_host(s, cfg, br.OUT_BINS | br.OUT_SPECTRA)
+    assert br.last_kernel() == "window_fft_warp"
+    done, ref = oracle.pipeline_batch_mt(s.reshape(1, -1), ocfg_from(oracle, cfg), os.cpu_count() or 1,
+                                         want=("bins", "spectra"))
+    assert done == bars - n + 1
+    assert np.array_equal(got["bins"], ref["bins"][0])
+    err = np.abs(got["spectra"] - ref["spectra"][0]).max(axis=1) / np.abs(ref["spectra"][0]).max(axis=1)
+    assert err.max() < REL_TOL
