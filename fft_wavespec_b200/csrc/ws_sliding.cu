@@ -36,6 +36,11 @@ namespace ws {
 using ws_slide::Plan;
 
 constexpr int kSlideThreads = 256;
+// N = 4096 has 255 chains per segment and room for one CTA per SM only (210 KB of shared memory):
+// when rows are produced it runs two segments on 512 threads so that 16 warps are resident instead
+// of 8 (rows only 92 -> 118, spectra + rows 71 -> 82 M spectra/s); the pure spectra writer is
+// faster with 8 warps (105 vs 96).
+__host__ __device__ constexpr int slide_threads(int n, bool captures) { return (n >= 4096 && captures) ? 512 : kSlideThreads; }
 
 struct SlideLayout {
     int x_doubles;      // staged samples (even count)
@@ -104,9 +109,10 @@ struct TopSink {
 };
 
 template <int N, bool SPEC, int CAP, int TOP>
-__global__ void __launch_bounds__(kSlideThreads, TOP == 3 ? 2 : 3)
+__global__ void __launch_bounds__(slide_threads(N, CAP != 0), N >= 4096 ? 1 : (TOP == 3 ? 2 : 3))
 sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NT = slide_threads(N, CAP != 0);
     double* x = reinterpret_cast<double*>(smem_raw);
     double2* arena = reinterpret_cast<double2*>(smem_raw + lay.arena_off);
     const int tid = threadIdx.x;
@@ -117,18 +123,18 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     const int nvalid = (int)((wend - w0) < pl.T ? (wend - w0) : pl.T);
 
     // 1. stage the tile (+ halo); beyond the series the samples only feed windows that are never stored
-    for (int i = tid; i < pl.x_len; i += kSlideThreads) {
+    for (int i = tid; i < pl.x_len; i += NT) {
         int64_t a = w0 + i;
         x[i] = (a < p.series_len) ? src[a] : 0.0;
     }
     __syncthreads();
     // 2. deepest level straight from the samples
-    ws_slide::bottom_level(tid, kSlideThreads, x, pl, p.tw, arena);
+    ws_slide::bottom_level(tid, NT, x, pl, p.tw, arena);
     __syncthreads();
     // 3. chain-free radix-8 passes down to level 3
     for (int i = pl.nst; i >= 2; i--) {
         ws_slide::SmemSink sink{arena + pl.off[i - 1], pl.stride[i - 1]};
-        ws_slide::direct_pass(tid, kSlideThreads, arena + pl.off[i], pl.stride[i], pl.Q[i], 1 << pl.lev[i - 1],
+        ws_slide::direct_pass(tid, NT, arena + pl.off[i], pl.stride[i], pl.Q[i], 1 << pl.lev[i - 1],
                               pl.P[i - 1], p.tw, pl.N, pl.lev[i - 1], sink);
         __syncthreads();
     }
@@ -143,15 +149,15 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     if (p.select == 1 && top.lo < 1) top.lo = 1;
     if (lay.band <= 0) { top.lo = 1; top.hi = 0; }      // empty band: capture nothing
     top.nvalid = nvalid;
-    if (TOP == 3) ws_slide::chain_pass<N>(tid, kSlideThreads, arena + pl.off[1], pl.T, pl.S, p.tw, top);
-    else ws_slide::chain_pass4<N>(tid, kSlideThreads, arena + pl.off[1], pl.T, pl.S, p.tw, top);
+    if (TOP == 3) ws_slide::chain_pass<N>(tid, NT, arena + pl.off[1], pl.T, pl.S, p.tw, top);
+    else ws_slide::chain_pass4<N>(tid, NT, arena + pl.off[1], pl.T, pl.S, p.tw, top);
     if (!want_sel) return;
     __syncthreads();
     // 5. selection + rows
     const int lane = tid & 31, warp = tid >> 5;
     const int64_t gw_tile = (int64_t)s * p.nwin + w0;
     if (lay.band <= 0) {
-        for (int wl = warp; wl < nvalid; wl += kSlideThreads / 32)    // empty band: every slot absent
+        for (int wl = warp; wl < nvalid; wl += NT / 32)    // empty band: every slot absent
             warp_select_emit(p, nullptr, nullptr, nullptr, gw_tile + wl);
         return;
     }
@@ -164,12 +170,12 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
         if (lay.Lg != 8) {
             // run-time group width: powers in shared memory for the K scan rounds (the 8-lane
             // network of the common case reads the captured bins directly)
-            for (int i = tid; i < nvalid * band; i += kSlideThreads) { double2 v = top.xb[i]; pwa[i] = v.x * v.x + v.y * v.y; }
+            for (int i = tid; i < nvalid * band; i += NT) { double2 v = top.xb[i]; pwa[i] = v.x * v.x + v.y * v.y; }
             __syncthreads();
         }
         const int wpb = 32 / lay.Lg;
-        double* stage = reinterpret_cast<double*>(ov + ((pl.T * pws * 8 + 15) & ~15)) + warp * 512;
-        for (int b0 = warp * wpb; b0 < nvalid; b0 += (kSlideThreads / 32) * wpb) {
+        double* stage = reinterpret_cast<double*>(ov + ((pl.T * pws * 8 + 15) & ~15)) + warp * (wpb * p.K * 16);   // wpb windows x K rows x <= 16 doubles
+        for (int b0 = warp * wpb; b0 < nvalid; b0 += (NT / 32) * wpb) {
             const int nb = (nvalid - b0) < wpb ? (nvalid - b0) : wpb;
             if (lay.Lg == 8)
                 warp_select_emit_batch<8>(p, nullptr, top.xb + b0 * band, band, lo, 8, nb, gw_tile + b0, stage);
@@ -180,10 +186,10 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     }
     // selection-sort rule (A7b) or K > 8: one warp per window
     double* pw = reinterpret_cast<double*>(ov);
-    for (int i = tid; i < nvalid * band; i += kSlideThreads) { double2 v = top.xb[i]; pw[i] = v.x * v.x + v.y * v.y; }
+    for (int i = tid; i < nvalid * band; i += NT) { double2 v = top.xb[i]; pw[i] = v.x * v.x + v.y * v.y; }
     __syncthreads();
     int* ord = reinterpret_cast<int*>(ov + pl.T * band * 8) + warp * band;
-    for (int wl = warp; wl < nvalid; wl += kSlideThreads / 32) {
+    for (int wl = warp; wl < nvalid; wl += NT / 32) {
         warp_select_emit(p, pw + wl * band - lo, top.xb + wl * band - lo, ord, gw_tile + wl);
         __syncwarp();
     }
@@ -290,7 +296,7 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
         case 512:  T = 64;  S = (any_sel && p.spectra) ? 4 : 8; break;
         case 1024: T = 32;  S = any_sel ? (p.spectra ? 2 : 4) : 1; break;
         case 2048: T = 16;  S = 2;  break;
-        case 4096: T = 16;  S = 1;  break;
+        case 4096: T = 16;  S = (any_sel || p.band_buf) ? 2 : 1; break;
         default: return false;
     }
     int top = 3;
@@ -313,7 +319,7 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
     // The band capture is written while level 3 is still being read: it may only reuse what lies
     // below level 3, otherwise it gets its own space after the work area.  The epilogue buffers
     // are used after the barrier that follows the top pass: they overlay the (dead) work area.
-    const int warps = kSlideThreads / 32;
+    const int warps = slide_threads(p.N, true) / 32;
     lay.epi_mode = 0;
     lay.Lg = 32;
     if (p.select == 0) {
@@ -324,7 +330,7 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
     }
     int ov_bytes;
     if (lay.epi_mode == 2) {
-        ov_bytes = ((pl.T * (lay.Lg == 8 ? 64 : lay.band) * 8 + 15) & ~15) + warps * 512 * 8;
+        ov_bytes = ((pl.T * (lay.Lg == 8 ? 64 : lay.band) * 8 + 15) & ~15) + warps * (32 / lay.Lg) * p.K * 16 * 8;
     } else {
         ov_bytes = pl.T * lay.band * 8 + warps * lay.band * 4;
     }
@@ -389,7 +395,7 @@ static cudaError_t launch_top(const Params& p, const Plan& pl, const SlideLayout
         if (e != cudaSuccess) return e;
     }
     dim3 grid((unsigned)((p.chunk_nwin + pl.T - 1) / pl.T), (unsigned)p.n_series);
-    sliding_shared_kernel<N, SPEC, CAP, TOP><<<grid, kSlideThreads, lay.total_bytes, stream>>>(p, pl, lay);
+    sliding_shared_kernel<N, SPEC, CAP, TOP><<<grid, slide_threads(N, CAP != 0), lay.total_bytes, stream>>>(p, pl, lay);
     return cudaGetLastError();
 }
 
