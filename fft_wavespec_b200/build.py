@@ -21,6 +21,7 @@ SOURCES = [
     ("ws_sliding.cu", []),
     ("ws_rows.cu", []),
     ("ws_inverse.cu", []),
+    ("ws_phase.cu", ["-fmad=false"]),
     ("ws_series.cu", ["-fmad=false"]),
     ("ws_pla.cu", ["-fmad=false"]),
     ("ws_zigzag.cu", ["-fmad=false"]),

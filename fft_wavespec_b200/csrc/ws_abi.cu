@@ -143,6 +143,7 @@ struct Session {
     // per-stream band hand-off buffer (ws_sliding.cu -> ws_rows.cu); work on one stream is ordered,
     // so one buffer per stream can be reused launch after launch without synchronising
     std::map<cudaStream_t, std::unique_ptr<DeviceBuf>> band_scratch;
+    std::map<cudaStream_t, std::unique_ptr<DeviceBuf>> phase_scratch;   // spectra of a window range (phase path)
 };
 Session g_s;
 
@@ -258,6 +259,7 @@ int run_pipeline(const double* d_series, int32_t n_series, int32_t series_len,
     p.series = d_series; p.series_stride = series_len; p.n_series = n_series; p.series_len = series_len;
     p.N = N; p.log2N = ilog2(N); p.hop = c->hop; p.K = c->top_k; p.row_stride = c->row_stride;
     p.nwin = nwin; p.win_offset = 0; p.chunk_nwin = nwin;
+    p.spec_nwin = nwin; p.spec_w0 = 0;
     // band: Legacy/...-gpuopt-nodetrend.mq5:540-542
     int lo = (int)std::ceil((double)N / c->max_period);
     int hi = (int)std::floor((double)N / c->min_period);
@@ -334,7 +336,9 @@ int run_pipeline(const double* d_series, int32_t n_series, int32_t series_len,
             g_launches++;
         }
     } else {
-        if (any_spectral) {
+        // FFT dispatch for one Params (whole series or a window range): the shared-butterfly sliding
+        // kernels for plain hop-1 windows, the per-window kernels otherwise
+        auto dispatch_fft = [&](const Params& p) -> int {
             const bool plain = c->hop == 1 && c->detrend == WAVESPEC_DETREND_NONE &&
                                c->window_type == WAVESPEC_WINDOW_NONE && !p.phase;
             if (plain && ws::sliding_shared_supported(p)) {
@@ -343,7 +347,7 @@ int run_pipeline(const double* d_series, int32_t n_series, int32_t series_len,
                 // (WAVESPEC_SPLIT=1).  Measured on B200 at N=1024 they are within 3 % of each
                 // other (profiles/README.md); the fused form needs no scratch and one launch.
                 static const bool split = getenv("WAVESPEC_SPLIT") != nullptr;
-                if (split && ws::rows_from_band_supported(p)) {
+                if (split && p.win_offset == 0 && p.chunk_nwin == nwin && ws::rows_from_band_supported(p)) {
                     // sliding kernel = pure streaming writer + compact band hand-off; the rows kernel
                     // selects at full occupancy (ws_rows.cu).  The hand-off buffer is bounded: series
                     // (and, for very long series, window ranges) are processed in chunks on one stream.
@@ -398,6 +402,52 @@ int run_pipeline(const double* d_series, int32_t n_series, int32_t series_len,
                 WS_CUDA(ws::launch_window_fft(p, st, &g_last_kernel), "window_fft kernel");
             }
             g_launches++;
+            return WAVESPEC_OK;
+        };
+        if (any_spectral) {
+            if (p.phase && ws::phase_from_spectra_supported(N)) {
+                // A6 behind the FFT: the phase chain only needs the window's spectrum, so the fastest
+                // FFT kernel runs without it and ws_phase.cu follows on the same stream — on the
+                // caller's spectra plane when there is one, else on a scratch plane per window range
+                Params q = p;
+                q.phase = nullptr;
+                if (p.spectra) {
+                    if ((rc = dispatch_fft(q))) return rc;
+                    WS_CUDA(ws::launch_phase_from_spectra(p.spectra, nwin, 0, n_series, 0, nwin, nwin, N, p.phase, st),
+                            "phase_chain kernel");
+                    g_launches++;
+                } else {
+                    int64_t chunk = (int64_t)(((size_t)2 << 30) / ((size_t)n_series * N * 8));
+                    if (const char* e = getenv("WAVESPEC_PHASE_CHUNK")) { long v = atol(e); if (v > 0) chunk = v; }   // test hook
+                    if (chunk < 1) chunk = 1;
+                    if (chunk > nwin) chunk = nwin;
+                    // per-stream scratch, kept between calls (work on a stream is ordered, so the next
+                    // call may reuse it without waiting)
+                    double* scratch_p = nullptr;
+                    {
+                        const size_t sbytes = (size_t)n_series * chunk * N * 8;
+                        std::lock_guard<std::mutex> lk(g_s.mu);
+                        auto& slot = g_s.phase_scratch[st];
+                        if (!slot) slot = std::make_unique<DeviceBuf>();
+                        if (slot->bytes < sbytes) {
+                            WS_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize(phase scratch)");
+                            WS_CUDA(slot->alloc(sbytes), "cudaMalloc(phase scratch spectra)");
+                        }
+                        scratch_p = slot->as<double>();
+                    }
+                    for (int64_t wa = 0; wa < nwin; wa += chunk) {
+                        const int64_t cn = (wa + chunk <= nwin) ? chunk : nwin - wa;
+                        q.win_offset = wa; q.chunk_nwin = cn;
+                        q.spectra = scratch_p; q.spec_nwin = chunk; q.spec_w0 = wa;
+                        if ((rc = dispatch_fft(q))) return rc;
+                        WS_CUDA(ws::launch_phase_from_spectra(scratch_p, chunk, wa, n_series, wa, cn, nwin, N,
+                                                              p.phase, st), "phase_chain kernel");
+                        g_launches++;
+                    }
+                }
+            } else {
+                if ((rc = dispatch_fft(p))) return rc;
+            }
         }
         if (want_trk) {
             const bool plain = c->hop == 1 && c->detrend == WAVESPEC_DETREND_NONE &&
@@ -657,6 +707,7 @@ void gpu_shutdown(void) {
     cudaDeviceSynchronize();
     g_s.jobs.clear();
     g_s.band_scratch.clear();
+    g_s.phase_scratch.clear();
     g_pool.trim();
     g_s.tw.clear(); g_s.win.clear(); g_s.apow.clear();
     for (auto s : g_s.streams) cudaStreamDestroy(s);

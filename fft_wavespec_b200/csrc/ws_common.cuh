@@ -32,7 +32,10 @@ struct Params {
     const double* wtab;        // window coefficients w[i], i = 0..N-1 (or nullptr)
     const double* apow;        // iir_alpha^j, j = 0..N-1 (or nullptr)
     const double* feed;        // optional pre-built per-window feed [n_series][nwin][N] (PLA), or nullptr
-    double* spectra;           // [n_series][nwin][N] interleaved, or nullptr
+    double* spectra;           // [n_series][spec_nwin][N] interleaved, or nullptr; window w of series s is row
+                               // s * spec_nwin + (w - spec_w0)  (spec_nwin = nwin, spec_w0 = 0 for a caller's
+                               // plane; a window-range scratch of the phase path uses its own stride)
+    int64_t spec_nwin, spec_w0;
     double* rows;              // [n_series][nwin][K][row_stride], or nullptr
     int32_t* bins;             // [n_series][nwin][K], or nullptr
     double* waves;             // [n_series][nwin][K] A8a, or nullptr

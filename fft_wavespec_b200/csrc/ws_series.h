@@ -41,6 +41,12 @@ cudaError_t launch_window_fft(Params p, cudaStream_t stream, const char** which 
 bool window_fft_warp_supported(const Params& p);
 cudaError_t launch_window_fft_warp(Params p, cudaStream_t stream);
 
+// ws_phase.cu: A6 phase chain of every window of a spectra plane (rows s * spec_nwin + (w - spec_w0))
+bool phase_from_spectra_supported(int N);
+cudaError_t launch_phase_from_spectra(const double* spectra, int64_t spec_nwin, int64_t spec_w0, int n_series,
+                                      int64_t win_offset, int64_t chunk_nwin, int64_t nwin, int N,
+                                      double* phase, cudaStream_t stream);
+
 // ws_sliding.cu
 bool sliding_shared_supported(const Params& p);
 // *which (when non-null) receives "sliding_overlap" if the producer / consumer form ran

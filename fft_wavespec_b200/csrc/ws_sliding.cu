@@ -141,7 +141,7 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     // 4. top pass: level 3 -> full spectra, streamed to HBM
     const bool want_sel = CAP == 1;
     TopSink<N, SPEC, CAP, TOP> top;
-    top.g = SPEC ? reinterpret_cast<double2*>(p.spectra) + ((int64_t)s * p.nwin + w0) * (N / 2) : nullptr;
+    top.g = SPEC ? reinterpret_cast<double2*>(p.spectra) + ((int64_t)s * p.spec_nwin + (w0 - p.spec_w0)) * (N / 2) : nullptr;
     top.xb = nullptr;
     if (CAP == 1 && lay.band > 0) top.xb = reinterpret_cast<double2*>(smem_raw + lay.xb_off);
     if (CAP == 2) top.xb = p.band_buf + ((int64_t)s * p.chunk_nwin + (w0 - p.win_offset)) * lay.band;
@@ -240,7 +240,7 @@ sliding_overlap_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     }
 
     TopSink<N, SPEC, 1, 3> top;
-    top.g = SPEC ? reinterpret_cast<double2*>(p.spectra) + ((int64_t)s * p.nwin + w0) * (N / 2) : nullptr;
+    top.g = SPEC ? reinterpret_cast<double2*>(p.spectra) + ((int64_t)s * p.spec_nwin + (w0 - p.spec_w0)) * (N / 2) : nullptr;
     top.xb = reinterpret_cast<double2*>(smem_raw + lay.xb_off);
     top.lo = p.band_lo; top.hi = p.band_hi; top.band = lay.band;
     top.nvalid = nvalid;

@@ -237,7 +237,7 @@ window_fft_kernel(const Params p) {
             out[(size_t)wl * M + k] = X;
             if (p.spectra) {
                 double2* g = reinterpret_cast<double2*>(
-                    p.spectra + (((int64_t)s * nwin + w0 + wb + wl)) * N);
+                    p.spectra + (((int64_t)s * p.spec_nwin + (w0 - p.spec_w0) + wb + wl)) * N);
                 g[k] = X;
             }
             if (p.band_buf && k >= p.band_lo && k <= p.band_hi)      // hand-off to the tracker / rows kernels

@@ -135,7 +135,8 @@ window_fft_warp_kernel(const Params p, const WarpLayout L) {
         __syncwarp();
 
         const int64_t gw = (int64_t)s * nwin + w0 + t;
-        double2* g = p.spectra ? reinterpret_cast<double2*>(p.spectra + gw * N) : nullptr;
+        double2* g = p.spectra
+            ? reinterpret_cast<double2*>(p.spectra + ((int64_t)s * p.spec_nwin + (w0 - p.spec_w0) + t) * N) : nullptr;
         double2* bb = p.band_buf
             ? p.band_buf + ((int64_t)s * p.chunk_nwin + (w0 - p.win_offset) + t) * nband - lo : nullptr;
         double* pwa = pwb - lo;

@@ -51,7 +51,9 @@ run("C3 IIR+Blackman (spectra+bins)", 2048, 4, 100000, S | B, top_k=8, min_perio
 run("C3 Kalman4D only", 2048, 256, 1000000, KA)
 run("C4 Hann+sort+waves+wkalman", 1024, 4, 100000, S | B | W | WK, top_k=8, min_period=12.0, max_period=256.0,
     window_type=br.WINDOW_HANN, select=br.SELECT_SORT)
-run("C4 phase chain", 1024, 2, 50000, PH, window_type=br.WINDOW_HANN)
+run("C4 phase chain (Hann)", 1024, 2, 50000, PH, window_type=br.WINDOW_HANN)
+run("C4 plain: phase+waves+rows", 1024, 4, 100000, PH | W | R, top_k=8, min_period=18.0, max_period=200.0)
+run("C4 plain: spectra+phase+rows", 1024, 4, 100000, S | PH | R, top_k=8, min_period=18.0, max_period=200.0)
 run("C5 N=4096 K=4 rows", 4096, 2, 200000, R, top_k=4, min_period=9.0, max_period=200.0)
 run("C5 N=4096 K=4 spectra+rows", 4096, 2, 200000, S | R, top_k=4, min_period=9.0, max_period=200.0)
 run("PLA feed + FFT", 1024, 1, 30000, S | B, feed=br.FEED_PLA)

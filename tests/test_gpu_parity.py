@@ -842,3 +842,52 @@ def test_config1_full_size_all_windows_against_oracle(br, oracle):
     assert np.array_equal(got["bins"], ref["bins"][0])
     err = np.abs(got["spectra"] - ref["spectra"][0]).max(axis=1) / np.abs(ref["spectra"][0]).max(axis=1)
     assert err.max() < REL_TOL
+
+
+# ---- A6 behind the FFT kernels (ws_phase.cu) ----------------------------------------------------
+def _check_phase_planes(got, ref):
+    gp, rp = got["phase"], ref["phase"]
+    dph = np.angle(np.exp(1j * (gp[:, 0] - rp[:, 0])))
+    assert np.abs(dph).max() < 1e-6
+    # unwrapped phase / group delay only where no step sits within 1e-6 of a +-pi jump decision
+    ph = rp[:, 0]
+    d = np.abs(np.abs(np.diff(ph, axis=1)) - np.pi)
+    safe = d.min(axis=1) > 1e-6
+    assert safe.sum() > 0.9 * safe.size
+    assert np.abs(gp[safe, 1] - rp[safe, 1]).max() < 1e-9 * max(1.0, np.abs(rp[safe, 1]).max())
+    assert np.abs(gp[safe, 2] - rp[safe, 2]).max() < 1e-9 * 100.0
+
+
+@pytest.mark.parametrize("with_spectra", [True, False])
+def test_phase_chain_behind_the_sliding_kernel(br, oracle, with_spectra, monkeypatch):
+    """Config-4 shape on plain hop-1 windows: the sliding kernel produces spectra + rows, the phase
+    kernel follows on the plane (the caller's, or a scratch plane walked in window ranges)."""
+    monkeypatch.setenv("WAVESPEC_PHASE_CHUNK", "37")          # several ragged window ranges
+    s = synth.random_walk(1500, 1024 + 300)
+    cfg = br.default_cfg(1024, top_k=8, min_period=18.0, max_period=200.0)
+    outs = br.OUT_PHASE | br.OUT_BINS | br.OUT_WAVES | br.OUT_ROWS | (br.OUT_SPECTRA if with_spectra else 0)
+    got, ref = run_both(br, oracle, s, cfg, outs)
+    assert br.last_kernel() in ("sliding_shared", "sliding_overlap")
+    check_planes(br, got, ref, cfg)
+    _check_phase_planes(got, ref)
+
+
+@pytest.mark.parametrize("n", [64, 512, 2048, 8192])
+def test_phase_chain_behind_the_per_window_kernels(br, oracle, n, monkeypatch):
+    monkeypatch.setenv("WAVESPEC_PHASE_CHUNK", "5")
+    s = synth.random_walk(1501 + n, n + 23)
+    cfg = br.default_cfg(n, top_k=4, min_period=9.0, max_period=200.0, detrend=br.DETREND_MEAN,
+                         window_type=br.WINDOW_HANN)
+    got, ref = run_both(br, oracle, s, cfg, br.OUT_PHASE | br.OUT_BINS)
+    check_planes(br, got, ref, cfg)
+    _check_phase_planes(got, ref)
+
+
+def test_phase_chain_two_series_batch(br, oracle):
+    s = synth.random_walk_batch(1510, 2, 1024 + 90)
+    cfg = br.default_cfg(1024, top_k=8, min_period=18.0, max_period=200.0)
+    got = br.pipeline_host(s, cfg, br.OUT_PHASE | br.OUT_SPECTRA)
+    for i in range(2):
+        ref = oracle.pipeline_series(s[i], ocfg_from(oracle, cfg), br.OUT_PHASE | br.OUT_SPECTRA)
+        _check_phase_planes({"phase": got["phase"][i]}, ref)
+        assert rel_err(got["spectra"][i], ref["spectra"]) < REL_TOL
