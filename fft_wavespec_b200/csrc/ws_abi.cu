@@ -134,6 +134,7 @@ struct Session {
     bool open = false;
     int device = 0;
     std::vector<cudaStream_t> streams;
+    cudaStream_t side = nullptr;       // Kalman4D runs here beside the FFT kernels of the same call
     std::atomic<uint32_t> rr{0};
     std::map<int, std::unique_ptr<DeviceBuf>> tw;                       // N -> exp(-2 pi i m/N)
     std::map<std::pair<int, int>, std::unique_ptr<DeviceBuf>> win;      // (N,type) -> w[i]
@@ -336,6 +337,29 @@ int run_pipeline(const double* d_series, int32_t n_series, int32_t series_len,
             g_launches++;
         }
     } else {
+        // Kalman4D (A9) only reads the series: it is one thread per series and strictly sequential over
+        // bars (0.7 s for 1M bars), so it is forked onto the session's side stream and runs beside the
+        // FFT kernels of this call; `st` joins it at the end.
+        cudaEvent_t kalman_join = nullptr;
+        if (d_kalman) {
+            ws::KalmanParams kp;
+            std::memcpy(&kp, &c->kalman, sizeof kp);
+            cudaStream_t ks = (g_s.side && (any_spectral || want_trk)) ? g_s.side : st;
+            if (ks != st) {
+                cudaEvent_t fork = nullptr;
+                WS_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming), "cudaEventCreate");
+                WS_CUDA(cudaEventRecord(fork, st), "cudaEventRecord(fork)");          // inputs are ready on st
+                WS_CUDA(cudaStreamWaitEvent(ks, fork, 0), "cudaStreamWaitEvent(fork)");
+                cudaEventDestroy(fork);
+            }
+            WS_CUDA(ws::launch_kalman4d(d_series + (N - 1), series_len, c->hop, n_series, nwin, kp, d_kalman, ks),
+                    "kalman4d kernel");
+            g_launches++;
+            if (ks != st) {
+                WS_CUDA(cudaEventCreateWithFlags(&kalman_join, cudaEventDisableTiming), "cudaEventCreate");
+                WS_CUDA(cudaEventRecord(kalman_join, ks), "cudaEventRecord(join)");
+            }
+        }
         // FFT dispatch for one Params (whole series or a window range): the shared-butterfly sliding
         // kernels for plain hop-1 windows, the per-window kernels otherwise
         auto dispatch_fft = [&](const Params& p) -> int {
@@ -454,12 +478,9 @@ int run_pipeline(const double* d_series, int32_t n_series, int32_t series_len,
                                c->window_type == WAVESPEC_WINDOW_NONE && !p.phase;
             if ((rc = run_tracker_path(p, c, d_trk_index, d_trk_period, plain, st))) return rc;
         }
-        if (d_kalman) {
-            ws::KalmanParams kp;
-            std::memcpy(&kp, &c->kalman, sizeof kp);
-            WS_CUDA(ws::launch_kalman4d(d_series + (N - 1), series_len, c->hop, n_series, nwin, kp, d_kalman, st),
-                    "kalman4d kernel");
-            g_launches++;
+        if (kalman_join) {
+            WS_CUDA(cudaStreamWaitEvent(st, kalman_join, 0), "cudaStreamWaitEvent(kalman)");
+            cudaEventDestroy(kalman_join);
         }
     }
     if (want_wk) {
@@ -695,6 +716,7 @@ int32_t gpu_init(int32_t device_index, int32_t stream_count) {
     int n = stream_count < 1 ? 1 : (stream_count > 32 ? 32 : stream_count);   // more CUDA streams buy nothing
     g_s.streams.resize(n);
     for (int i = 0; i < n; i++) WS_CUDA(cudaStreamCreateWithFlags(&g_s.streams[i], cudaStreamNonBlocking), "cudaStreamCreate");
+    WS_CUDA(cudaStreamCreateWithFlags(&g_s.side, cudaStreamNonBlocking), "cudaStreamCreate(side)");
     g_s.device = device_index;
     g_s.open = true;
     return WAVESPEC_OK;
@@ -711,6 +733,7 @@ void gpu_shutdown(void) {
     g_pool.trim();
     g_s.tw.clear(); g_s.win.clear(); g_s.apow.clear();
     for (auto s : g_s.streams) cudaStreamDestroy(s);
+    if (g_s.side) { cudaStreamDestroy(g_s.side); g_s.side = nullptr; }
     g_s.streams.clear();
     g_s.open = false;
 }

@@ -49,6 +49,10 @@ run("C2 plain top-8", 1024, 4, 300000, S | R, top_k=8, min_period=18.0, max_peri
 run("C3 IIR+Blackman (spectra+bins)", 2048, 4, 100000, S | B, top_k=8, min_period=18.0, max_period=52.0,
     detrend=br.DETREND_IIR, trend_period=1024.0, window_type=br.WINDOW_BLACKMAN)
 run("C3 Kalman4D only", 2048, 256, 1000000, KA)
+run("C3 bins + Kalman4D (side stream)", 2048, 64, 200000, B | KA, top_k=8, min_period=18.0, max_period=52.0,
+    detrend=br.DETREND_IIR, trend_period=1024.0, window_type=br.WINDOW_BLACKMAN)
+run("C3 bins only (same shape)", 2048, 64, 200000, B, top_k=8, min_period=18.0, max_period=52.0,
+    detrend=br.DETREND_IIR, trend_period=1024.0, window_type=br.WINDOW_BLACKMAN)
 run("C4 Hann+sort+waves+wkalman", 1024, 4, 100000, S | B | W | WK, top_k=8, min_period=12.0, max_period=256.0,
     window_type=br.WINDOW_HANN, select=br.SELECT_SORT)
 run("C4 phase chain (Hann)", 1024, 2, 50000, PH, window_type=br.WINDOW_HANN)
