@@ -153,10 +153,28 @@ def run_reference(args):
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit_json(out)
 
 
 # --------------------------------------------------------------------------------------------------
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line.  Native libraries write there too (NCCL prints its
+    version banner to fd 1 whenever NCCL_DEBUG is set on the box), so the real stdout is kept aside
+    for the JSON line and fd 1 is pointed at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_json(obj):
+    print(json.dumps(obj), file=_JSON_OUT if _JSON_OUT is not None else sys.stdout, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -171,6 +189,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
@@ -187,9 +206,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to
-        # stdout whenever NCCL_DEBUG is set on the box) goes to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     st = bridge.gpu_init(local_rank, 8)
     if st != bridge.OK:
@@ -336,7 +352,7 @@ def main():
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                "clocks": clocks, "extra": {"rows_only_spectra_per_s": rows_only,
                                            "rows_only_kernel": "ws::" + bridge.last_kernel() + "_kernel"}}
-        print(json.dumps(out), flush=True)
+        emit_json(out)
     bridge.gpu_shutdown()
     if world > 1:
         dist.destroy_process_group()
