@@ -7,7 +7,7 @@ for n in 256 512 1024 2048 4096; do python profiles/prof_k1.py $n | tail -1; don
 echo "# same with WAVESPEC_K1W=0 (CTA-per-window-group kernel only)"
 for n in 512 1024 2048; do WAVESPEC_K1W=0 python profiles/prof_k1.py $n | tail -1; done
 echo "# BASELINE config shapes (prof_configs.py)"
-python profiles/prof_configs.py 2>&1 | tail -14
+python profiles/prof_configs.py 2>&1 | tail -22
 } > gpurun_out/k1/timings.txt 2>&1
 cat gpurun_out/k1/timings.txt
 for n in 512 1024 2048; do
