@@ -47,9 +47,20 @@ phase_chain_kernel(const double2* __restrict__ spec, int64_t spec_nwin, int64_t 
         const int64_t s = item / chunk_nwin, j = item - s * chunk_nwin;
         const int64_t w = win_offset + j;
         const double2* X = spec + (s * spec_nwin + (w - spec_w0)) * M;
-        for (int k = lane; k < M; k += 32) {
-            const double2 x = __ldcs(X + k);
-            ph[pad_idx(k, lc)] = atan2(x.y, x.x);
+        // eight 16-byte loads in flight per lane before the first atan2 (its branches keep the
+        // compiler from hoisting the loads of later iterations by itself)
+        for (int k0 = 0; k0 < M; k0 += 256) {
+            double2 xr[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int k = k0 + lane + 32 * u;
+                xr[u] = k < M ? __ldcs(X + k) : make_double2(1.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int k = k0 + lane + 32 * u;
+                if (k < M) ph[pad_idx(k, lc)] = atan2(xr[u].y, xr[u].x);
+            }
         }
         __syncwarp();
         // local prefix of the increments of bins [lane C, lane C + C)
