@@ -292,7 +292,7 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
     const bool any_sel = (p.bins || p.rows || p.waves || p.contrib) && !p.band_buf;
     int T, S;
     switch (p.N) {
-        case 256:  T = 128; S = 16; break;
+        case 256:  T = 128; S = (any_sel && p.spectra) ? 4 : 16; break;
         case 512:  T = 64;  S = (any_sel && p.spectra) ? 4 : 8; break;
         case 1024: T = 32;  S = any_sel ? (p.spectra ? 2 : 4) : 1; break;
         case 2048: T = 16;  S = 2;  break;
