@@ -12,9 +12,14 @@ weak scaling: every rank owns its own 64 series (series shard with no collective
 path); torch.distributed/NCCL only carries the barrier and the max-over-ranks time.
 
   value        device-resident inputs, CUDA-event time over exactly K steps, max over ranks
-  e2e          the same metric through the imports.mqh API (gpu_submit_extract_cycles_batch /
-               gpu_try_get_cycles_batch / gpu_free_job) with pinned HOST buffers: H2D of every
-               series and D2H of every result row inside the timed region
+  e2e          the same metric through the job API with pinned HOST buffers, H2D of every series
+               and D2H of every result inside the timed region, for both job products:
+               `e2e`      the cycle-cache record (wavespec_submit_cycle_cache_batch: what the 1.1.0
+                          warm-up keeps of a batch, 20 doubles per bar, decoded on the device)
+               `e2e_rows` the unmodified imports.mqh calls (gpu_submit_extract_cycles_batch /
+                          gpu_try_get_cycles_batch / gpu_free_job: top_k x 15 doubles per window)
+  parity_check windows of the TIMED run's own output (rows of every launch group, spectra of the
+               last group's ring) compared with the oracle after the timed region
   roofline     algorithmic HBM bytes of the dominant kernel / its measured duration, against
                MEASURED_PEAKS.json
   cpu_baseline the oracle (line-faithful port of the reference's CPU path) on the host cores,
@@ -41,6 +46,8 @@ N_WINDOW = 1024
 TOP_K = 8
 MIN_P, MAX_P = 18.0, 200.0
 ROW_STRIDE = 15
+CPU_NOTE = ("the CPU arm computes every window's FFT, power spectrum and top-8 selection (bins) but stores "
+            "neither the spectra plane nor the result rows: less work than the GPU arm does per window")
 
 
 def config_dict(n_series, bars, gpus):
@@ -128,6 +135,136 @@ def cpu_oracle_rate(n_series, target_seconds, threads):
     return done / dt, f"first {per_series} windows of {ns} series of config 2 ({done} spectra, {dt:.1f} s)", (series, cfg)
 
 
+
+def gpu_numa_cpus(local_rank):
+    """CPUs of the NUMA node the GPU hangs off (None when the box does not say)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        return node, (cpus & os.sched_getaffinity(0)) or None
+    except Exception:
+        return None, None
+
+
+def parity_check(orc, host_np, cfg_o, d_rows, d_spectra, S, G, nwin, rng_seed=1234):
+    """Reads windows of the timed run's output back and compares them with the oracle: selected
+    bins exact, amplitude / energy and spectra within 1e-9 relative.  Rows: 64 windows spread over
+    all series (every launch group); spectra: 8 windows of the ring, i.e. of the last group."""
+    import torch
+    rng = np.random.default_rng(rng_seed)
+    res = {"rows_windows": 0, "spectra_windows": 0, "bins_equal": True, "max_rel_err_amplitude": 0.0,
+           "max_rel_err_spectra": 0.0, "tolerance": 1e-9}
+    picks = [(int(s), int(w)) for s, w in zip(rng.integers(0, S, 64), rng.integers(0, nwin, 64))]
+    picks += [(0, 0), (S - 1, nwin - 1)]
+    for s, w in picks:
+        rows = d_rows[s, w].cpu().numpy()
+        ref = orc.pipeline_series(host_np[s, w:w + N_WINDOW], cfg_o, orc.OUT_ROWS | orc.OUT_BINS)
+        bins = np.rint(N_WINDOW / rows[:, 2]).astype(np.int64)
+        res["bins_equal"] &= bool(np.array_equal(bins, ref["bins"][0]))
+        for f in (0, 6):
+            r = ref["rows"][0][:, f]
+            res["max_rel_err_amplitude"] = max(res["max_rel_err_amplitude"],
+                                               float(np.abs(rows[:, f] - r).max() / np.abs(r).max()))
+        res["rows_windows"] += 1
+    last0 = ((S - 1) // G) * G                                 # first series of the last launch group
+    for i in range(8):
+        g = int(rng.integers(0, S - last0)); w = int(rng.integers(0, nwin))
+        spec = d_spectra[g, w].cpu().numpy()
+        ref = orc.pipeline_series(host_np[last0 + g, w:w + N_WINDOW], cfg_o, orc.OUT_SPECTRA)["spectra"][0]
+        res["max_rel_err_spectra"] = max(res["max_rel_err_spectra"], float(np.abs(spec - ref).max() / np.abs(ref).max()))
+        res["spectra_windows"] += 1
+    res["ok"] = bool(res["bins_equal"] and res["max_rel_err_amplitude"] <= 1e-9 and res["max_rel_err_spectra"] <= 1e-9)
+    res["rows_series_sampled"] = len({s for s, _ in picks})
+    return res
+
+
+def e2e_pass(bridge, host_np, outs, submit, getter, units_per_job):
+    """One pass over every series through the job API, as the reference's callers drive it
+    (submit, poll try_get, free; WaveCyclesBatchFetcher.mq5:113-133) with `len(outs)` jobs in
+    flight.  Every job's result lands in a pinned host buffer and one value of it is read."""
+    from collections import deque
+    S = host_np.shape[0]
+    pending, free_bufs, i, done, acc = deque(), list(range(len(outs))), 0, 0, 0.0
+    while done < S:
+        while i < S and free_bufs:
+            stt, jid = submit(host_np[i])
+            if stt != bridge.OK:
+                raise RuntimeError(f"submit failed {stt}: {bridge.last_error()}")
+            b = free_bufs.pop()
+            getter(jid, outs[b])                       # first poll arms the buffer: chunks land as they finish
+            pending.append((jid, b)); i += 1
+        jid, b = pending[0]
+        stt, n, ready = getter(jid, outs[b])
+        if stt != bridge.OK:
+            raise RuntimeError(f"try_get failed {stt}: {bridge.last_error()}")
+        if ready:
+            assert n == units_per_job, (n, units_per_job)
+            acc += float(outs[b][0]) + float(outs[b][-1])
+            bridge.gpu_free_job(jid)
+            pending.popleft(); free_bufs.append(b); done += 1
+        else:
+            time.sleep(0.0002)
+    return acc
+
+
+def live_path_numbers(bridge, synth):
+    """The per-bar calls of the 1.1.0 live loop (WaveSpecZZ_1.1.0-gpuopt.mq5:1249, :1313-1392)."""
+    x = synth.random_walk(5, N_WINDOW)
+    out = np.empty(N_WINDOW)
+    res = {}
+    for _ in range(20):
+        bridge.gpu_fft_real_forward(x, out)
+    t = time.perf_counter()
+    for _ in range(300):
+        bridge.gpu_fft_real_forward(x, out)
+    res["gpu_fft_real_forward_1024_us"] = 1e6 * (time.perf_counter() - t) / 300
+    for _ in range(20):
+        bridge.gpu_extract_cycles(x, 2, 9.0, 200.0)
+    t = time.perf_counter()
+    for _ in range(300):
+        bridge.gpu_extract_cycles(x, 2, 9.0, 200.0)
+    res["gpu_extract_cycles_1024_us"] = 1e6 * (time.perf_counter() - t) / 300
+    # async submit / poll at depth 64 (InpAsyncDepth), one job per bar
+    series = synth.random_walk(6, N_WINDOW + 4096)
+    buf = np.zeros((2, 15))
+    def run(nbars):
+        jobs, got = [], 0
+        for b in range(nbars):
+            stt, jid = bridge.gpu_submit_extract_cycles(series[b:b + N_WINDOW], 2, 9.0, 200.0, 60.0, 0, 10)
+            assert stt == bridge.OK
+            jobs.append(jid)
+            keep = []
+            for j in jobs:                                 # poll everything queued (:1267-1310)
+                stt, n, ready = bridge.gpu_try_get_cycles(j, buf, 15, 2)
+                if stt == bridge.OK and ready:
+                    bridge.gpu_free_job(j); got += 1
+                else:
+                    keep.append(j)
+            jobs = keep
+            while len(jobs) >= 64:                         # queue full: wait for the oldest (:1342-1374)
+                stt, n, ready = bridge.gpu_try_get_cycles(jobs[0], buf, 15, 2)
+                if stt == bridge.OK and ready:
+                    bridge.gpu_free_job(jobs.pop(0)); got += 1
+        while jobs:
+            stt, n, ready = bridge.gpu_try_get_cycles(jobs[0], buf, 15, 2)
+            if stt == bridge.OK and ready:
+                bridge.gpu_free_job(jobs.pop(0)); got += 1
+        return got
+    run(256)
+    t = time.perf_counter()
+    got = run(4096)
+    res["async_depth64_bars_per_s"] = got / (time.perf_counter() - t)
+    return res
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle port; MQL5 cannot be
     compiled or run here) on all host threads, same metric/config."""
@@ -150,7 +287,8 @@ def run_reference(args):
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": config_dict(64, 1000000, args.gpus),
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                            "note": CPU_NOTE},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit_json(out)
@@ -186,7 +324,9 @@ def main():
     ap.add_argument("--group", type=int, default=4, help="series per kernel launch (spectra ring size)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--e2e-depth", type=int, default=4, help="jobs in flight in the e2e legs")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     claim_stdout()
@@ -205,6 +345,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # host side of the PCIe path: run this rank (and allocate its pinned buffers, first touch) on the
+    # CPUs of the NUMA node its GPU hangs off
+    all_cpus = os.sched_getaffinity(0)
+    numa_node, numa_cpus = gpu_numa_cpus(local_rank)
+    if numa_cpus:
+        os.sched_setaffinity(0, numa_cpus)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     st = bridge.gpu_init(local_rank, 8)
@@ -238,6 +384,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
     def timed(nsteps, **kw):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -247,12 +400,7 @@ def main():
             step(**kw)
         e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, bridge.launch_count() - l0
+        return max_over_ranks(e0.elapsed_time(e1)), bridge.launch_count() - l0
 
     for _ in range(args.warmup):
         step()
@@ -268,11 +416,19 @@ def main():
     spectra_per_step = S * nwin
     value = world * spectra_per_step * args.steps / (ms * 1e-3)
 
+    # ---- the timed run's own output against the oracle ---------------------------------------------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import oracle as orc
+        cfg_o = orc.default_cfg(N_WINDOW, top_k=TOP_K, min_period=MIN_P, max_period=MAX_P, row_stride=ROW_STRIDE)
+        parity = parity_check(orc, host_np, cfg_o, d_rows, d_spectra, S, G, nwin)
+
     # rows-only product (P2) for reference: same kernel, spectra store disabled
     for _ in range(2):
         step(with_spectra=False)
     ms_rows, _ = timed(max(2, args.steps // 2), with_spectra=False)
     rows_only = world * spectra_per_step * max(2, args.steps // 2) / (ms_rows * 1e-3)
+    rows_kernel = bridge.last_kernel()
 
     peak, peak_src = load_peaks()
     alg_bytes = 8 * 1 + 8 * N_WINDOW                       # 8*hop in + 8*N out per spectrum
@@ -284,74 +440,80 @@ def main():
                 "algorithmic_bytes_per_spectrum": alg_bytes, "spectra_per_launch": G * nwin,
                 "avg_launch_ms": launch_ms,
                 "note": "rows (960 B/window) are extra traffic not counted in the algorithmic bytes"}
-    prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(prof):
-        try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        prof = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(prof):
+            try:
+                roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+                roofline["traffic_source"] = f"profiles/{name} (ncu --set full capture of this launch shape, not measured in this run)"
+                break
+            except Exception:
+                pass
 
-    # ---- e2e: the imports.mqh job API with pinned host buffers -----------------------------------
-    e2e = None
+    # the big device planes are not needed any more: the job API below allocates its own
+    del d_spectra, d_rows
+    torch.cuda.empty_cache()
+
+    # ---- e2e: the job API with pinned host buffers --------------------------------------------------
+    e2e = e2e_rows = None
     if not args.no_e2e:
+        depth = args.e2e_depth
+
+        def measure(submit, getter, out_doubles, units, d2h_bytes):
+            outs = [torch.empty(out_doubles, dtype=torch.float64, pin_memory=True).numpy() for _ in range(depth)]
+            e2e_pass(bridge, host_np, outs, submit, getter, units)         # warm-up (pools, pinned pages)
+            barrier()
+            tt = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                e2e_pass(bridge, host_np, outs, submit, getter, units)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - tt)
+            del outs
+            return {"value": world * spectra_per_step * args.e2e_steps / dt, "unit": UNIT,
+                    "h2d_bytes_per_step": world * S * T * 8, "d2h_bytes_per_step": world * S * d2h_bytes,
+                    "ms_per_step": 1e3 * dt / args.e2e_steps, "jobs_in_flight": depth,
+                    "d2h_gb_per_s_per_gpu": S * d2h_bytes * args.e2e_steps / dt / 1e9}
+
+        e2e = measure(lambda x: bridge.submit_cycle_cache_batch(x, N_WINDOW, 1, TOP_K, MIN_P, MAX_P, 60.0, 0, 10),
+                      bridge.try_get_cycle_cache, T * 20, T, T * 20 * 8)
+        e2e["product"] = ("cycle-cache record: 20 doubles per bar (WaveSpecZZ_1.1.0-gpuopt.mq5:294-324), extraction and "
+                          "the decode of :1067-1099 on the device")
+        e2e["api"] = "wavespec_submit_cycle_cache_batch / wavespec_try_get_cycle_cache / gpu_free_job, pinned host buffers"
         out_doubles = nwin * TOP_K * ROW_STRIDE
-        outs = [torch.empty(out_doubles, dtype=torch.float64, pin_memory=True).numpy() for _ in range(2)]
-        depth = 4
+        e2e_rows = measure(lambda x: bridge.gpu_submit_extract_cycles_batch(x, N_WINDOW, 1, TOP_K, MIN_P, MAX_P, 60.0,
+                                                                           0, 10, ROW_STRIDE),
+                           bridge.gpu_try_get_cycles_batch, out_doubles, nwin * TOP_K, out_doubles * 8)
+        e2e_rows["product"] = "stride-15 rows: top_k x 15 doubles per window (960 B/window), PCIe bound"
+        e2e_rows["api"] = "gpu_submit_extract_cycles_batch / gpu_try_get_cycles_batch / gpu_free_job (imports.mqh), pinned host buffers"
+        pcie = os.path.join(ROOT, "profiles", "r02_pcie_ceiling.json")
+        if os.path.exists(pcie):
+            try:
+                ceil = json.load(open(pcie))
+                e2e_rows["d2h_ceiling_gb_per_s_per_gpu"] = ceil.get(str(world), ceil.get("1"))
+                e2e_rows["d2h_ceiling_source"] = "profiles/r02_pcie_ceiling.json (probe_pcie.py, ranks concurrently)"
+            except Exception:
+                pass
 
-        def e2e_step():
-            pending, got_rows, k = [], 0, 0
-            def drain():
-                nonlocal got_rows, k
-                jid = pending.pop(0)
-                while True:
-                    stt, n, ready = bridge.gpu_try_get_cycles_batch(jid, outs[k % 2], out_doubles)
-                    if stt == bridge.OK and ready:
-                        break
-                    if stt != bridge.NOT_READY:
-                        raise RuntimeError(f"try_get failed {stt}: {bridge.last_error()}")
-                    time.sleep(0.0002)
-                bridge.gpu_free_job(jid)
-                got_rows += n; k += 1
-            for i in range(S):
-                stt, jid = bridge.gpu_submit_extract_cycles_batch(host_np[i], N_WINDOW, 1, TOP_K, MIN_P, MAX_P, 60.0,
-                                                                  0, 10, ROW_STRIDE)
-                if stt != bridge.OK:
-                    raise RuntimeError(f"submit failed {stt}: {bridge.last_error()}")
-                pending.append(jid)
-                if len(pending) >= depth:
-                    drain()
-            while pending:
-                drain()
-            assert got_rows == S * nwin * TOP_K
-        e2e_step()                                         # warm-up
-        barrier()
-        tt = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - tt
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": world * spectra_per_step * args.e2e_steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": world * S * T * 8, "d2h_bytes_per_step": world * S * out_doubles * 8,
-               "api": "gpu_submit_extract_cycles_batch / gpu_try_get_cycles_batch / gpu_free_job, pinned host buffers",
-               "ms_per_step": 1e3 * dt / args.e2e_steps}
-
+    live = None
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        rate, sample, _ = cpu_oracle_rate(S, args.cpu_seconds, threads)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+    if rank == 0 and world == 1:
+        if not args.no_e2e:
+            live = live_path_numbers(bridge, synth)
+        if not args.no_cpu:
+            os.sched_setaffinity(0, all_cpus)
+            threads = os.cpu_count() or 1
+            rate, sample, _ = cpu_oracle_rate(S, args.cpu_seconds, threads)
+            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "note": CPU_NOTE}
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(S, T, world),
-               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-               "clocks": clocks, "extra": {"rows_only_spectra_per_s": rows_only,
-                                           "rows_only_kernel": "ws::" + bridge.last_kernel() + "_kernel"}}
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_rows": e2e_rows,
+               "parity_check": parity, "gpu_launches": int(launches), "clocks": clocks,
+               "extra": {"rows_only_spectra_per_s": rows_only, "rows_only_kernel": "ws::" + rows_kernel + "_kernel",
+                         "live_path": live, "numa_node": numa_node,
+                         "host_cpus_bound": len(numa_cpus) if numa_cpus else None}}
         emit_json(out)
     bridge.gpu_shutdown()
     if world > 1:

@@ -23,6 +23,7 @@ DETREND_NONE, DETREND_IIR, DETREND_MEAN = 0, 1, 2
 WINDOW_NONE, WINDOW_HANN, WINDOW_HAMMING, WINDOW_BLACKMAN, WINDOW_BARTLETT, WINDOW_HANN_WIP = range(6)
 SELECT_INSERTION, SELECT_SORT = 0, 1
 OUT_SPECTRA, OUT_ROWS, OUT_BINS, OUT_WAVES, OUT_KALMAN, OUT_PHASE, OUT_WKALMAN, OUT_TRACKER = 1, 2, 4, 8, 16, 32, 64, 128
+OUT_CONTRIB = 256
 ROW_FIELDS = 15
 
 
@@ -50,6 +51,12 @@ class CacheParams(C.Structure):
     """wavespec_cache_params (include/wavespec_abi.h)."""
     _fields_ = [("music_only", C.c_int32), ("use_music_weights", C.c_int32), ("min_coherence", C.c_double),
                 ("min_score", C.c_double), ("min_snr_db", C.c_double)]
+
+
+class Planes(C.Structure):
+    """wavespec_planes (include/wavespec_abi.h): output pointers, NULL = not wanted."""
+    _fields_ = [(n, C.c_void_p) for n in ("spectra", "rows", "bins", "waves", "contrib", "kalman", "phase",
+                                          "wkalman", "trk_index", "trk_period")]
 
 
 class WaveSpecError(RuntimeError):
@@ -106,6 +113,23 @@ def lib():
     L.wavespec_applied_price_device.restype = i32
     L.wavespec_cycle_cache_host.argtypes = [vp, i32, i32, i32, i32, i32, i32, dbl, C.POINTER(CacheParams), vp]
     L.wavespec_cycle_cache_host.restype = i32
+    L.wavespec_pipeline_host_planes.argtypes = [vp, i32, i32, C.POINTER(PipelineCfg), C.POINTER(Planes)]
+    L.wavespec_pipeline_host_planes.restype = i32
+    L.wavespec_pipeline_device_planes.argtypes = [vp, i32, i32, C.POINTER(PipelineCfg), C.POINTER(Planes), vp]
+    L.wavespec_pipeline_device_planes.restype = i32
+    L.wavespec_fft_real_inverse_batch_host.argtypes = [vp, i32, i32, vp]
+    L.wavespec_fft_real_inverse_batch_host.restype = i32
+    L.wavespec_fft_real_inverse_batch_device.argtypes = [vp, i32, i64, vp, vp]
+    L.wavespec_fft_real_inverse_batch_device.restype = i32
+    L.wavespec_try_get_cycles_batch64.argtypes = [i64, vp, i64, C.POINTER(i64), _ip]
+    L.wavespec_try_get_cycles_batch64.restype = i32
+    L.wavespec_submit_cycle_cache_batch.argtypes = [vp, i32, i32, i32, i32, dbl, dbl, dbl, i32, i32,
+                                                    C.POINTER(CacheParams), C.POINTER(i64)]
+    L.wavespec_submit_cycle_cache_batch.restype = i32
+    L.wavespec_try_get_cycle_cache.argtypes = [i64, vp, i64, _ip, _ip]
+    L.wavespec_try_get_cycle_cache.restype = i32
+    L.wavespec_device_count.argtypes = []; L.wavespec_device_count.restype = i32
+    L.wavespec_job_device.argtypes = [i64]; L.wavespec_job_device.restype = i32
     L.wavespec_launch_count.argtypes = []; L.wavespec_launch_count.restype = i64
     L.wavespec_last_kernel.argtypes = []; L.wavespec_last_kernel.restype = C.c_char_p
     L.wavespec_version.argtypes = []; L.wavespec_version.restype = i32
@@ -122,6 +146,10 @@ EXPORTED_SYMBOLS = [
     "wavespec_cycle_cache_host", "wavespec_applied_price_host", "wavespec_applied_price_device",
     "wavespec_launch_count",
     "wavespec_last_kernel", "wavespec_version",
+    "wavespec_pipeline_host_planes", "wavespec_pipeline_device_planes",
+    "wavespec_fft_real_inverse_batch_host", "wavespec_fft_real_inverse_batch_device",
+    "wavespec_try_get_cycles_batch64", "wavespec_submit_cycle_cache_batch", "wavespec_try_get_cycle_cache",
+    "wavespec_device_count", "wavespec_job_device",
 ]
 
 
@@ -226,6 +254,44 @@ def gpu_free_job(job_id) -> int:
     return lib().gpu_free_job(job_id)
 
 
+def try_get_cycles_batch64(job_id, out):
+    n = C.c_int64(0); ready = C.c_int32(0)
+    st = lib().wavespec_try_get_cycles_batch64(job_id, _ptr(out), out.size, C.byref(n), C.byref(ready))
+    return st, n.value, ready.value
+
+
+def submit_cycle_cache_batch(series, window_len, hop, top_k, min_period, max_period, sample_rate_seconds=60.0,
+                             method=0, ar_order=10, music_only=False, use_music_weights=False,
+                             min_coherence=0.05, min_score=0.01, min_snr_db=-40.0):
+    """Cycle cache record (20 doubles per bar, WaveSpecZZ_1.1.0-gpuopt.mq5:294-324) as a job product."""
+    x = _f64(series); jid = C.c_int64(0)
+    cp = CacheParams(int(music_only), int(use_music_weights), min_coherence, min_score, min_snr_db)
+    st = lib().wavespec_submit_cycle_cache_batch(_ptr(x), x.size, window_len, hop, top_k, min_period, max_period,
+                                                 sample_rate_seconds, method, ar_order, C.byref(cp), C.byref(jid))
+    return st, jid.value
+
+
+def try_get_cycle_cache(job_id, out):
+    n = C.c_int32(0); ready = C.c_int32(0)
+    st = lib().wavespec_try_get_cycle_cache(job_id, _ptr(out), out.size, C.byref(n), C.byref(ready))
+    return st, n.value, ready.value
+
+
+def device_count() -> int:
+    return lib().wavespec_device_count()
+
+
+def job_device(job_id) -> int:
+    return lib().wavespec_job_device(job_id)
+
+
+def fft_real_inverse_batch(spec, window_len):
+    s = _f64(spec).reshape(-1, window_len)
+    out = np.empty_like(s)
+    _check(lib().wavespec_fft_real_inverse_batch_host(_ptr(s), window_len, s.shape[0], _ptr(out)))
+    return out
+
+
 # ---- new-build extensions -----------------------------------------------------------------------
 def default_cfg(window_len, **over) -> PipelineCfg:
     cfg = PipelineCfg()
@@ -258,23 +324,23 @@ def pipeline_host(series, cfg: PipelineCfg, outputs=None):
         "wkalman": np.empty((ns, nw)) if outputs & OUT_WKALMAN else None,
         "trk_index": np.empty((ns, nw, 12), dtype=np.int32) if outputs & OUT_TRACKER else None,
         "trk_period": np.empty((ns, nw, 12)) if outputs & OUT_TRACKER else None,
+        "contrib": np.empty((ns, nw, K)) if outputs & OUT_CONTRIB else None,
     }
-    st = lib().wavespec_pipeline_host(_ptr(s2), ns, sl, C.byref(cfg), _ptr(o["spectra"]), _ptr(o["rows"]),
-                                      _ptr(o["bins"]), _ptr(o["waves"]), _ptr(o["kalman"]),
-                                      _ptr(o["phase"]), _ptr(o["wkalman"]), _ptr(o["trk_index"]),
-                                      _ptr(o["trk_period"]))
+    pl = Planes(**{k: (None if v is None else v.ctypes.data) for k, v in o.items()})
+    st = lib().wavespec_pipeline_host_planes(_ptr(s2), ns, sl, C.byref(cfg), C.byref(pl))
     _check(st)
     return {k: (v[0] if squeeze else v) for k, v in o.items() if v is not None}
 
 
 def pipeline_device(d_series, n_series, series_len, cfg: PipelineCfg, spectra=0, rows=0, bins=0, waves=0,
-                    kalman=0, phase=0, wkalman=0, trk_index=0, trk_period=0, stream=0):
+                    kalman=0, phase=0, wkalman=0, trk_index=0, trk_period=0, contrib=0, stream=0):
     """Device-pointer pipeline; every buffer is a raw device address (e.g. torch.Tensor.data_ptr())."""
     vp = C.c_void_p
-    st = lib().wavespec_pipeline_device(vp(d_series), n_series, series_len, C.byref(cfg), vp(spectra or None),
-                                        vp(rows or None), vp(bins or None), vp(waves or None),
-                                        vp(kalman or None), vp(phase or None), vp(wkalman or None),
-                                        vp(trk_index or None), vp(trk_period or None), vp(stream or None))
+    pl = Planes(spectra=spectra or None, rows=rows or None, bins=bins or None, waves=waves or None,
+                contrib=contrib or None, kalman=kalman or None, phase=phase or None, wkalman=wkalman or None,
+                trk_index=trk_index or None, trk_period=trk_period or None)
+    st = lib().wavespec_pipeline_device_planes(vp(d_series), n_series, series_len, C.byref(cfg), C.byref(pl),
+                                               vp(stream or None))
     _check(st)
 
 

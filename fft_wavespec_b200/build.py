@@ -16,6 +16,9 @@ OUT = os.path.join(HERE, "libwavespec.so")
 # bit-identical to the CPU statement: no FMA contraction there.
 SOURCES = [
     ("ws_abi.cu", []),
+    ("ws_runtime.cu", []),
+    ("ws_jobs.cu", []),
+    ("ws_pipeline.cu", []),
     ("ws_window_fft.cu", []),
     ("ws_window_fft_warp.cu", []),
     ("ws_sliding.cu", []),
@@ -56,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if r.returncode:
                 raise RuntimeError(f"nvcc failed on {src}")
     if force or _stale(OUT, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", OUT] + objs + ["-lcudart"]
+        cmd = [nvcc] + ARCH + ["-shared", "-o", OUT] + objs + ["-lcudart", "-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)

@@ -51,10 +51,10 @@ __device__ __forceinline__ CacheRow decode(const double* row, int k, double peri
 }
 
 __global__ void cycle_cache_kernel(const double* __restrict__ rows, int64_t n_windows, int32_t top_k, int32_t stride,
-                                   int32_t N, int32_t hop, int64_t bars, double period_seconds,
-                                   const wavespec_cache_params cp, double* __restrict__ out) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= bars) return;
+                                   int32_t N, int32_t hop, int64_t bars, int64_t bar0, int64_t nbars,
+                                   double period_seconds, const wavespec_cache_params cp, double* __restrict__ out) {
+    const int64_t idx = bar0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= bar0 + nbars || idx >= bars) return;
     CacheRow b1, b2;
     b1.ok = false; b2.ok = false;
     int64_t w = idx / hop;
@@ -91,10 +91,12 @@ __global__ void cycle_cache_kernel(const double* __restrict__ rows, int64_t n_wi
 }
 
 cudaError_t launch_cycle_cache(const double* rows, int64_t n_windows, int32_t top_k, int32_t stride, int32_t N,
-                               int32_t hop, int64_t bars, double period_seconds, const wavespec_cache_params& cp,
-                               double* out, cudaStream_t stream) {
-    const unsigned blocks = (unsigned)((bars + 255) / 256);
-    cycle_cache_kernel<<<blocks, 256, 0, stream>>>(rows, n_windows, top_k, stride, N, hop, bars, period_seconds, cp, out);
+                               int32_t hop, int64_t bars, int64_t bar0, int64_t nbars, double period_seconds,
+                               const wavespec_cache_params& cp, double* out, cudaStream_t stream) {
+    if (nbars < 1) return cudaSuccess;
+    const unsigned blocks = (unsigned)((nbars + 255) / 256);
+    cycle_cache_kernel<<<blocks, 256, 0, stream>>>(rows, n_windows, top_k, stride, N, hop, bars, bar0, nbars,
+                                                   period_seconds, cp, out);
     return cudaGetLastError();
 }
 

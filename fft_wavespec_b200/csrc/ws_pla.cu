@@ -147,29 +147,32 @@ pla_kernel(const double* __restrict__ series, int64_t series_stride, int64_t nwi
     }
 }
 
-static int32_t* g_pla_overflow = nullptr;
-
+// `overflow` is a device int the caller has zeroed on `stream`; it is set when a window's recursion
+// outgrew the on-chip stack (the caller reads it back before it trusts the feed).
 cudaError_t launch_pla(const double* series, int64_t series_stride, int32_t n_series, int64_t nwin,
                        int32_t N, int32_t hop, int32_t max_segments, double max_error, double* lines,
-                       int32_t* seg_bounds, int32_t* seg_counts, int32_t bounds_cap,
+                       int32_t* seg_bounds, int32_t* seg_counts, int32_t bounds_cap, int32_t* overflow,
                        cudaStream_t stream) {
-    if (!g_pla_overflow) {
-        cudaError_t e = cudaMalloc(&g_pla_overflow, sizeof(int32_t));
-        if (e != cudaSuccess) return e;
-    }
-    cudaError_t e = cudaMemsetAsync(g_pla_overflow, 0, sizeof(int32_t), stream);
-    if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((nwin + 31) / 32), (unsigned)n_series);
     pla_kernel<<<grid, 32, 0, stream>>>(series, series_stride, nwin, N, hop, max_segments, max_error,
-                                        lines, seg_bounds, seg_counts, bounds_cap, g_pla_overflow);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    int32_t ov = 0;
-    e = cudaMemcpyAsync(&ov, g_pla_overflow, sizeof ov, cudaMemcpyDeviceToHost, stream);
-    if (e != cudaSuccess) return e;
-    e = cudaStreamSynchronize(stream);
-    if (e != cudaSuccess) return e;
-    return ov ? cudaErrorAssert : cudaSuccess;   // recursion deeper than kPlaStack / kPlaSegCap
+                                        lines, seg_bounds, seg_counts, bounds_cap, overflow);
+    return cudaGetLastError();
+}
+
+// z[s][wa + w] = feed[s][w][N-1]: the newest sample of every PLA line is the Kalman4D measurement
+// (Legacy/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:3354-3360)
+__global__ void gather_last_kernel(const double* __restrict__ feed, int64_t cn, int32_t N, double* __restrict__ z,
+                                   int64_t z_stride, int64_t wa) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (w < cn) z[(int64_t)s * z_stride + wa + w] = feed[((int64_t)s * cn + w) * N + (N - 1)];
+}
+
+cudaError_t launch_gather_last(const double* feed, int32_t n_series, int64_t cn, int32_t N, double* z,
+                               int64_t z_stride, int64_t wa, cudaStream_t stream) {
+    dim3 grid((unsigned)((cn + 255) / 256), (unsigned)n_series);
+    gather_last_kernel<<<grid, 256, 0, stream>>>(feed, cn, N, z, z_stride, wa);
+    return cudaGetLastError();
 }
 
 }  // namespace ws

@@ -67,8 +67,10 @@ cudaError_t launch_wkalman(const double* contrib, const int32_t* bins, const dou
 // ws_pla.cu
 cudaError_t launch_pla(const double* series, int64_t series_stride, int32_t n_series, int64_t nwin,
                        int32_t N, int32_t hop, int32_t max_segments, double max_error, double* lines,
-                       int32_t* seg_bounds, int32_t* seg_counts, int32_t bounds_cap,
+                       int32_t* seg_bounds, int32_t* seg_counts, int32_t bounds_cap, int32_t* overflow,
                        cudaStream_t stream);
+cudaError_t launch_gather_last(const double* feed, int32_t n_series, int64_t cn, int32_t N, double* z,
+                               int64_t z_stride, int64_t wa, cudaStream_t stream);
 
 // ws_zigzag.cu
 cudaError_t launch_applied_price(const double* o, const double* h, const double* l, const double* c, int64_t n,
@@ -79,9 +81,10 @@ cudaError_t launch_zigzag(const double* zmain, const double* zhigh, const double
                           cudaStream_t stream);
 
 // ws_cache.cu
+// bars [bar0, bar0 + nbars) of the per-bar cache record; `rows` holds every window of the series
 cudaError_t launch_cycle_cache(const double* rows, int64_t n_windows, int32_t top_k, int32_t stride, int32_t N,
-                               int32_t hop, int64_t bars, double period_seconds, const ::wavespec_cache_params& cp,
-                               double* out, cudaStream_t stream);
+                               int32_t hop, int64_t bars, int64_t bar0, int64_t nbars, double period_seconds,
+                               const ::wavespec_cache_params& cp, double* out, cudaStream_t stream);
 
 // ws_inverse.cu
 cudaError_t launch_inverse_real(const double* d_spec, int32_t N, int32_t n_windows, const double2* tw,

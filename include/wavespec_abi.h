@@ -63,7 +63,12 @@ enum {
  * ---------------------------------------------------------------------------------- */
 
 /* imports.mqh:6.  Idempotent lazy session on CUDA device `device_index`; `stream_count`
- * (2 in Legacy, 16..512 in 1.1.0 :729-735, 64 in the Fetcher :105-106) sizes the stream pool. */
+ * (2 in Legacy, 16..512 in 1.1.0 :729-735, 64 in the Fetcher :105-106) sizes the stream pool.
+ * Every opened device keeps its own session (streams, coefficient tables, memory pools, one host
+ * worker thread).  device_index = -1 opens every device of the box; calling gpu_init again with
+ * another index adds that device.  With several devices open, submitted jobs are bound to the
+ * devices round robin (series shard over GPUs, no collective) and the synchronous
+ * calls run on the first opened device. */
 WAVESPEC_API int32_t gpu_init(int32_t device_index, int32_t stream_count);
 
 /* imports.mqh:7.  Waits for in-flight jobs, frees every job and the session. */
@@ -94,7 +99,7 @@ WAVESPEC_API int32_t gpu_submit_extract_cycles(const double* series, int32_t len
 
 /* imports.mqh:14.  Non-blocking poll: WAVESPEC_NOT_READY with *ready=0 while running
  * (the only "still running" answer the 1.1.0 wait loop :1342-1374 accepts), WAVESPEC_OK with
- * *ready=1 and rows copied when done. */
+ * *ready=1 and rows copied when done.  Never waits for the device. */
 WAVESPEC_API int32_t gpu_try_get_cycles(int64_t job_id, double* out, int32_t out_stride,
                                         int32_t out_capacity, int32_t* out_len, int32_t* ready);
 
@@ -109,11 +114,23 @@ WAVESPEC_API int32_t gpu_submit_extract_cycles_batch(const double* series, int32
                                                      int64_t* job_id);
 
 /* imports.mqh:18.  out_cap counts DOUBLES, *out_len counts ROWS
- * (WaveSpecZZ_1.1.0-gpuopt.mq5:1016-1017, :1067-1089). */
+ * (WaveSpecZZ_1.1.0-gpuopt.mq5:1016-1017, :1067-1089).  While the job runs the answer is WAVESPEC_OK
+ * with *ready=0: WaveCyclesBatchFetcher.mq5:127-132 sleeps only on that answer (NOT_READY would make
+ * it spin through its 4000 tries), and the 1.1.0 warm-up loop (:1029-1040) accepts it too.
+ * The poll never waits for the device.  The first poll arms `out`: the job's result is copied into
+ * it chunk by chunk while later chunks are still being computed (directly by DMA when `out` is
+ * page-locked), so keep polling with the same buffer; *ready=1 means every row has landed.  A
+ * batch is limited to 2^31-1 rows / doubles by the int32 arguments (wavespec_try_get_cycles_batch64
+ * lifts that). */
 WAVESPEC_API int32_t gpu_try_get_cycles_batch(int64_t job_id, double* out, int32_t out_cap,
                                               int32_t* out_len, int32_t* ready);
 
-/* imports.mqh:19.  Any job kind, finished or in flight. */
+/* same with 64-bit capacity and row count */
+WAVESPEC_API int32_t wavespec_try_get_cycles_batch64(int64_t job_id, double* out, int64_t out_cap,
+                                                     int64_t* out_len, int32_t* ready);
+
+/* imports.mqh:19.  Any job kind, finished or in flight (an in-flight job keeps running; its device
+ * memory returns to the pool in stream order, result copies into `out` are waited for). */
 WAVESPEC_API int32_t gpu_free_job(int64_t job_id);
 
 /* imports.mqh:20.  Copies the calling thread's last error text as UTF-16; returns the number
@@ -157,9 +174,25 @@ enum {
     WAVESPEC_OUT_KALMAN  = 16,  /* nwin doubles: StepKalman4D on the newest window sample */
     WAVESPEC_OUT_PHASE   = 32,  /* nwin * 3 * window_len/2 doubles: phase, unwrapped, group delay */
     WAVESPEC_OUT_WKALMAN = 64,  /* nwin doubles: weight-Kalman blend (1.0.4-kalman.mq5:194-231) */
-    WAVESPEC_OUT_TRACKER = 128  /* nwin * 12 int32 bins + nwin * 12 double periods: the stable slots of
+    WAVESPEC_OUT_TRACKER = 128, /* nwin * 12 int32 bins + nwin * 12 double periods: the stable slots of
                                    the period tracker pool (Legacy/...-kalman-fast.mq5:1415-1667)  */
+    WAVESPEC_OUT_CONTRIB = 256  /* nwin * top_k doubles: A8b single-bin inverse DFT at the newest sample
+                                   (Legacy/WaveSpecZZ_1.0.4-kalman.mq5:182-192), the weight-Kalman input */
 };
+
+/* Output planes of the *_planes pipeline entry points (NULL = not wanted); layouts as above. */
+typedef struct wavespec_planes {
+    double*  spectra;
+    double*  rows;
+    int32_t* bins;
+    double*  waves;
+    double*  contrib;
+    double*  kalman;
+    double*  phase;
+    double*  wkalman;
+    int32_t* trk_index;
+    double*  trk_period;
+} wavespec_planes;
 
 /* Kalman4D parameters, defaults of Legacy/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:885-901 */
 typedef struct wavespec_kalman4d_params {
@@ -212,6 +245,23 @@ WAVESPEC_API int32_t wavespec_pipeline_device(const double* d_series, int32_t n_
                                               double* d_waves, double* d_kalman, double* d_phase,
                                               double* d_wkalman, int32_t* d_trk_index,
                                               double* d_trk_period, void* stream);
+
+/* Same two calls with the planes in a struct (adds the A8b contribution plane). */
+WAVESPEC_API int32_t wavespec_pipeline_host_planes(const double* series, int32_t n_series, int32_t series_len,
+                                                   const wavespec_pipeline_cfg* cfg,
+                                                   const wavespec_planes* planes);
+WAVESPEC_API int32_t wavespec_pipeline_device_planes(const double* d_series, int32_t n_series,
+                                                     int32_t series_len, const wavespec_pipeline_cfg* cfg,
+                                                     const wavespec_planes* planes, void* stream);
+
+/* Batched form of gpu_fft_real_inverse (Legacy/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:27, used
+ * Legacy/WaveSpecZZ_1.0.4-core.mq5:426): n_windows half spectra of window_len interleaved doubles
+ * each (the layout gpu_fft_real_forward_batch and the spectra plane produce) -> n_windows *
+ * window_len real samples, 1/window_len normalised.  The device form enqueues on `stream`. */
+WAVESPEC_API int32_t wavespec_fft_real_inverse_batch_host(const double* in_spec, int32_t window_len,
+                                                          int32_t n_windows, double* out);
+WAVESPEC_API int32_t wavespec_fft_real_inverse_batch_device(const double* d_spec, int32_t window_len,
+                                                            int64_t n_windows, double* d_out, void* stream);
 
 /* Sliding variant of gpu_fft_real_forward_batch (hop-spaced overlapping windows of one host
  * series) — named distinctly, as SURVEY.md section 8b requires. */
@@ -276,6 +326,25 @@ WAVESPEC_API int32_t wavespec_cycle_cache_host(const double* rows, int32_t n_win
                                                int32_t stride, int32_t window_len, int32_t hop,
                                                int32_t bars, double period_seconds,
                                                const wavespec_cache_params* params, double* out);
+
+/* The cycle cache record as a JOB PRODUCT: same arguments as
+ * gpu_submit_extract_cycles_batch plus the indicator's weighting inputs; the sliding extraction and
+ * the decode of WaveSpecZZ_1.1.0-gpuopt.mq5:1067-1099 both run on the device and only the record
+ * SaveCycleCache writes (:294-324) crosses PCIe: 20 doubles per BAR (160 B) instead of top_k * 15
+ * doubles per window.  Poll with wavespec_try_get_cycle_cache (out_cap in doubles, *out_bars in
+ * bars; same non-blocking, chunked delivery as gpu_try_get_cycles_batch), release with gpu_free_job. */
+WAVESPEC_API int32_t wavespec_submit_cycle_cache_batch(const double* series, int32_t series_len,
+                                                       int32_t window_len, int32_t hop, int32_t top_k,
+                                                       double min_period, double max_period,
+                                                       double sample_rate_seconds, int32_t method,
+                                                       int32_t ar_order, const wavespec_cache_params* params,
+                                                       int64_t* job_id);
+WAVESPEC_API int32_t wavespec_try_get_cycle_cache(int64_t job_id, double* out, int64_t out_cap,
+                                                  int32_t* out_bars, int32_t* ready);
+
+/* Devices opened by gpu_init, and the device a job was bound to (-1: unknown job). */
+WAVESPEC_API int32_t wavespec_device_count(void);
+WAVESPEC_API int32_t wavespec_job_device(int64_t job_id);
 
 /* Number of kernels launched by this library since gpu_init (bench.py `gpu_launches`). */
 WAVESPEC_API int64_t wavespec_launch_count(void);

@@ -43,6 +43,20 @@ def near_ties(spectra, lo, hi, k, gap=1e-11):
     return int(np.sum(np.abs(a - b) <= gap * np.maximum(a, 1e-300)))
 
 
+def poll_batch(br, jid, out, tries=4000, sleep_s=0.005, getter=None):
+    """The poll loop of WaveCyclesBatchFetcher.mq5:127-132: a running batch job must answer OK with
+    ready == 0 (the Fetcher sleeps only on that answer; anything else ends its loop)."""
+    import time
+    getter = getter or br.gpu_try_get_cycles_batch
+    for _ in range(tries):
+        st, n, ready = getter(jid, out)
+        if st == br.OK and ready == 1:
+            return st, n, ready
+        assert st == br.OK and ready == 0, (st, br.last_error())
+        time.sleep(sleep_s)
+    raise AssertionError("batch job did not finish within the Fetcher's poll budget")
+
+
 def ocfg_from(oracle, cfg):
     o = oracle.PipelineCfg()
     C.memmove(C.byref(o), C.byref(cfg), C.sizeof(o))
@@ -213,11 +227,7 @@ def test_config5_n4096_batch_api(br, oracle):
     assert st == br.OK and jid != 0, br.last_error()
     nwin = 301
     out = np.zeros(nwin * 4 * 15)
-    for _ in range(20000):
-        st, n, ready = br.gpu_try_get_cycles_batch(jid, out)
-        if st == br.OK and ready:
-            break
-        assert st == br.NOT_READY
+    st, n, ready = poll_batch(br, jid, out)
     assert ready == 1 and n == nwin * 4
     assert br.gpu_free_job(jid) == br.OK
     cfg = oracle.default_cfg(4096, top_k=4, min_period=9.0, max_period=200.0, sample_rate_seconds=60.0)
@@ -622,10 +632,7 @@ def test_full_size_series_1m_bars_properties(br, oracle):
     assert st == br.OK
     nwin = bars - n + 1
     out = np.empty(nwin * 8 * 15)
-    for _ in range(2000000):
-        st, cnt, ready = br.gpu_try_get_cycles_batch(jid, out)
-        if st != br.NOT_READY:
-            break
+    st, cnt, ready = poll_batch(br, jid, out, sleep_s=0.001)
     assert st == br.OK and ready == 1 and cnt == nwin * 8
     assert br.gpu_free_job(jid) == br.OK
     rows = out.reshape(nwin, 8, 15)
