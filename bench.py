@@ -521,4 +521,10 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)        # jobs may be in flight and worker threads parked: no orderly teardown after an error

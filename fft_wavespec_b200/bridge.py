@@ -121,6 +121,10 @@ def lib():
     L.wavespec_fft_real_inverse_batch_host.restype = i32
     L.wavespec_fft_real_inverse_batch_device.argtypes = [vp, i32, i64, vp, vp]
     L.wavespec_fft_real_inverse_batch_device.restype = i32
+    L.wavespec_reconstruct_topk_host.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.wavespec_reconstruct_topk_host.restype = i32
+    L.wavespec_reconstruct_topk_device.argtypes = [vp, vp, i32, i32, i64, vp, vp]
+    L.wavespec_reconstruct_topk_device.restype = i32
     L.wavespec_try_get_cycles_batch64.argtypes = [i64, vp, i64, C.POINTER(i64), _ip]
     L.wavespec_try_get_cycles_batch64.restype = i32
     L.wavespec_submit_cycle_cache_batch.argtypes = [vp, i32, i32, i32, i32, dbl, dbl, dbl, i32, i32,
@@ -150,6 +154,7 @@ EXPORTED_SYMBOLS = [
     "wavespec_fft_real_inverse_batch_host", "wavespec_fft_real_inverse_batch_device",
     "wavespec_try_get_cycles_batch64", "wavespec_submit_cycle_cache_batch", "wavespec_try_get_cycle_cache",
     "wavespec_device_count", "wavespec_job_device",
+    "wavespec_reconstruct_topk_host", "wavespec_reconstruct_topk_device",
 ]
 
 
@@ -390,6 +395,17 @@ def cycle_cache_host(rows, top_k, window_len, hop, bars, period_seconds=60.0, mu
     out = np.empty((bars, 20))
     _check(lib().wavespec_cycle_cache_host(_ptr(r2), n_windows, top_k, stride, window_len, hop, bars,
                                            float(period_seconds), C.byref(cp), _ptr(out)))
+    return out
+
+
+def reconstruct_topk(spectra, bins):
+    """Inverse FFT of every window's spectrum masked to its selected bins: [nwin, N] samples."""
+    s = _f64(spectra)
+    n = s.shape[-1]
+    s2 = s.reshape(-1, n)
+    b = np.ascontiguousarray(bins, dtype=np.int32).reshape(s2.shape[0], -1)
+    out = np.empty_like(s2)
+    _check(lib().wavespec_reconstruct_topk_host(_ptr(s2), _ptr(b), n, b.shape[1], s2.shape[0], _ptr(out)))
     return out
 
 

@@ -231,25 +231,28 @@ int32_t wavespec_fft_real_forward_sliding(const double* series, int32_t series_l
     return fft_forward_common(series, window_len, hop, series_len, out);
 }
 
-int32_t wavespec_fft_real_inverse_batch_device(const double* d_spec, int32_t window_len, int64_t n_windows,
-                                               double* d_out, void* stream) {
+static int inverse_device_impl(const double* d_spec, const int32_t* d_bins, int32_t top_k, int32_t window_len,
+                               int64_t n_windows, double* d_out, void* stream) {
     Device* dev = device_of_pointer(d_spec);
     if (!dev) return g_rt.devs.empty() ? WAVESPEC_BACKEND_UNAVAILABLE : WAVESPEC_BAD_ARGS;
     if (!d_spec || !d_out) return fail(WAVESPEC_BAD_ARGS, "null buffer");
     if (!is_pow2(window_len) || window_len < 4 || window_len > 8192)
         return fail(WAVESPEC_BAD_ARGS, "window_len must be a power of two in [4, 8192]");
     if (n_windows < 1) return fail(WAVESPEC_BAD_ARGS, "n_windows must be >= 1");
+    if (d_bins && (top_k < 1 || top_k > ws::kMaxTopK)) return fail(WAVESPEC_BAD_ARGS, "top_k must be in [1, 32]");
     DeviceGuard guard(dev->index);
     const double2* tw;
     int rc = dev->get_twiddles(window_len, &tw);
     if (rc) return rc;
-    WS_CUDA(ws::launch_inverse_real(d_spec, window_len, n_windows, tw, d_out, static_cast<cudaStream_t>(stream)),
-            "inverse_real kernel");
+    WS_CUDA(ws::launch_inverse_real(d_spec, window_len, n_windows, tw, d_out, static_cast<cudaStream_t>(stream),
+                                    d_bins, top_k), "inverse_real kernel");
     g_launches++;
+    g_last_kernel = "inverse_real_warp";
     return WAVESPEC_OK;
 }
 
-int32_t wavespec_fft_real_inverse_batch_host(const double* in_spec, int32_t window_len, int32_t n_windows, double* out) {
+static int inverse_host_impl(const double* in_spec, const int32_t* bins, int32_t top_k, int32_t window_len,
+                             int32_t n_windows, double* out) {
     Device* dev = primary_device();
     if (!dev) return WAVESPEC_BACKEND_UNAVAILABLE;
     if (!in_spec || !out) return fail(WAVESPEC_BAD_ARGS, "null buffer");
@@ -259,15 +262,41 @@ int32_t wavespec_fft_real_inverse_batch_host(const double* in_spec, int32_t wind
     DeviceGuard guard(dev->index);
     cudaStream_t st = dev->pick_stream();
     const size_t bytes = (size_t)window_len * n_windows * 8;
-    AsyncBuf din, dout;
+    AsyncBuf din, dout, dbins;
     WS_CUDA(din.alloc(bytes, st), "cudaMallocAsync");
     WS_CUDA(dout.alloc(bytes, st), "cudaMallocAsync");
     WS_CUDA(cudaMemcpyAsync(din.p, in_spec, bytes, cudaMemcpyHostToDevice, st), "H2D spectrum");
-    int rc = wavespec_fft_real_inverse_batch_device(din.as<double>(), window_len, n_windows, dout.as<double>(), st);
+    if (bins) {
+        WS_CUDA(dbins.alloc((size_t)n_windows * top_k * 4, st), "cudaMallocAsync(bins)");
+        WS_CUDA(cudaMemcpyAsync(dbins.p, bins, dbins.bytes, cudaMemcpyHostToDevice, st), "H2D bins");
+    }
+    int rc = inverse_device_impl(din.as<double>(), dbins.as<int32_t>(), top_k, window_len, n_windows, dout.as<double>(), st);
     if (rc) { cudaStreamSynchronize(st); cudaGetLastError(); return rc; }
     WS_CUDA(cudaMemcpyAsync(out, dout.p, bytes, cudaMemcpyDeviceToHost, st), "D2H samples");
     WS_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
     return WAVESPEC_OK;
+}
+
+int32_t wavespec_fft_real_inverse_batch_device(const double* d_spec, int32_t window_len, int64_t n_windows,
+                                               double* d_out, void* stream) {
+    return inverse_device_impl(d_spec, nullptr, 0, window_len, n_windows, d_out, stream);
+}
+
+int32_t wavespec_fft_real_inverse_batch_host(const double* in_spec, int32_t window_len, int32_t n_windows, double* out) {
+    return inverse_host_impl(in_spec, nullptr, 0, window_len, n_windows, out);
+}
+
+int32_t wavespec_reconstruct_topk_device(const double* d_spectra, const int32_t* d_bins, int32_t window_len,
+                                         int32_t top_k, int64_t n_windows, double* d_out, void* stream) {
+    if (!d_bins) return fail(WAVESPEC_BAD_ARGS, "bins is null");
+    return inverse_device_impl(d_spectra, d_bins, top_k, window_len, n_windows, d_out, stream);
+}
+
+int32_t wavespec_reconstruct_topk_host(const double* spectra, const int32_t* bins, int32_t window_len,
+                                       int32_t top_k, int32_t n_windows, double* out) {
+    if (!bins) return fail(WAVESPEC_BAD_ARGS, "bins is null");
+    if (top_k < 1 || top_k > ws::kMaxTopK) return fail(WAVESPEC_BAD_ARGS, "top_k must be in [1, 32]");
+    return inverse_host_impl(spectra, bins, top_k, window_len, n_windows, out);
 }
 
 int32_t gpu_fft_real_inverse(const double* in_spec, int32_t len, double* out) {
@@ -318,7 +347,8 @@ int32_t gpu_try_get_cycles(int64_t job_id, double* out, int32_t out_stride, int3
     if (out_stride < 1 || out_capacity < 0) return fail(WAVESPEC_BAD_ARGS, "bad out_stride / out_capacity");
     if (!out_len) return fail(WAVESPEC_BAD_ARGS, "null output pointer");
     int64_t n = 0;
-    return narrow_len(try_get_job(job_id, out, out_capacity, out_stride, kJobWindow, &n, ready), n, out_len);
+    const int rc = try_get_job(job_id, out, out_capacity, out_stride, kJobWindow, &n, ready);
+    return narrow_len(rc, n, out_len);
 }
 
 int32_t gpu_submit_extract_cycles_batch(const double* series, int32_t series_len, int32_t window_len,
@@ -340,7 +370,8 @@ int32_t gpu_try_get_cycles_batch(int64_t job_id, double* out, int32_t out_cap, i
     if (out_cap < 0) return fail(WAVESPEC_BAD_ARGS, "bad out_cap");
     if (!out_len) return fail(WAVESPEC_BAD_ARGS, "null output pointer");
     int64_t n = 0;
-    return narrow_len(try_get_job(job_id, out, out_cap, 0, kJobBatchRows, &n, ready), n, out_len);
+    const int rc = try_get_job(job_id, out, out_cap, 0, kJobBatchRows, &n, ready);
+    return narrow_len(rc, n, out_len);
 }
 
 int32_t wavespec_try_get_cycles_batch64(int64_t job_id, double* out, int64_t out_cap, int64_t* out_len,
@@ -371,7 +402,8 @@ int32_t wavespec_try_get_cycle_cache(int64_t job_id, double* out, int64_t out_ca
     if (out_cap < 0) return fail(WAVESPEC_BAD_ARGS, "bad out_cap");
     if (!out_bars) return fail(WAVESPEC_BAD_ARGS, "null output pointer");
     int64_t n = 0;
-    return narrow_len(try_get_job(job_id, out, out_cap, 0, kJobCacheRecord, &n, ready), n, out_bars);
+    const int rc = try_get_job(job_id, out, out_cap, 0, kJobCacheRecord, &n, ready);
+    return narrow_len(rc, n, out_bars);
 }
 
 // ---- feeds ---------------------------------------------------------------------------------------

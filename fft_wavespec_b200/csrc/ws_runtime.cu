@@ -9,7 +9,10 @@ namespace wsrt {
 thread_local std::string t_last_error;
 std::atomic<int64_t> g_launches{0};
 std::atomic<const char*> g_last_kernel{"none"};
-Runtime g_rt;
+// Never destroyed: at process exit the CUDA runtime may already be gone when static destructors
+// run, and the worker threads are still parked on their queues.  gpu_shutdown is the orderly way
+// down; a process that exits without it simply drops everything.
+Runtime& g_rt = *new Runtime;
 
 int fail(int code, const std::string& msg) { t_last_error = msg; return code; }
 

@@ -170,7 +170,7 @@ struct Runtime {
     int64_t next_job = 1;
     std::atomic<uint32_t> rr_dev{0};
 };
-extern Runtime g_rt;
+extern Runtime& g_rt;
 
 // device lookup: nullptr (and last error set) when no device is open
 Device* primary_device();

@@ -87,7 +87,9 @@ cudaError_t launch_cycle_cache(const double* rows, int64_t n_windows, int32_t to
                                const ::wavespec_cache_params& cp, double* out, cudaStream_t stream);
 
 // ws_inverse.cu
-cudaError_t launch_inverse_real(const double* d_spec, int32_t N, int32_t n_windows, const double2* tw,
-                                double* d_out, cudaStream_t stream);
+// d_bins (optional, [n_windows][K] int32, -1 = absent): keep only these bins of each window's spectrum
+cudaError_t launch_inverse_real(const double* d_spec, int32_t N, int64_t n_windows, const double2* tw,
+                                double* d_out, cudaStream_t stream, const int32_t* d_bins = nullptr,
+                                int32_t K = 0);
 
 }  // namespace ws

@@ -199,4 +199,39 @@ WF_HD void split_phase(int lane, const double2* Z, const double2* tw, Sink sink)
     }
 }
 
+// ---- inverse real transform on the same passes ---------------------------------------------------
+// With Z = E + iO the M-point spectrum of z[m] = x[2m] + i x[2m+1],
+//     E[k] = (X[k] + conj X[M-k]) / 2,   O[k] = (X[k] - conj X[M-k]) / 2 * e^{+2 pi i k / N},
+// and z = conj(FFT(conj Z)) / M.  inverse_unpack writes conj Z[k] and conj Z[M-k] (swizzled) from
+// the pair xa = X[k], xb = X[M-k] (the caller passes xb = 0 for k = 0: the Nyquist bin is not part
+// of the contract; k = 0 and k = M/2 are self-paired); after the forward passes inverse_pair reads
+// (x[2m], x[2m+1]).
+template <int LN>
+WF_HD void inverse_unpack(int k, double2 xa, double2 xb, const double2* tw, double2* Z) {
+    typedef Geo<LN> G;
+    const int km = (G::M - k) & (G::M - 1);
+    const double2 wa = ld_tw(tw + k);                                       // e^{-2 pi i k / N}
+    {
+        const double2 E = make_double2(0.5 * (xa.x + xb.x), 0.5 * (xa.y - xb.y));
+        const double2 D = make_double2(0.5 * (xa.x - xb.x), 0.5 * (xa.y + xb.y));
+        const double2 O = make_double2(D.x * wa.x + D.y * wa.y, D.y * wa.x - D.x * wa.y);   // D * conj(wa)
+        Z[swz(k)] = make_double2(E.x - O.y, -(E.y + O.x));                                  // conj(E + iO)
+    }
+    if (k != 0 && k != G::M / 2) {
+        const double2 wb = ld_tw(tw + km);
+        const double2 E = make_double2(0.5 * (xb.x + xa.x), 0.5 * (xb.y - xa.y));
+        const double2 D = make_double2(0.5 * (xb.x - xa.x), 0.5 * (xb.y + xa.y));
+        const double2 O = make_double2(D.x * wb.x + D.y * wb.y, D.y * wb.x - D.x * wb.y);
+        Z[swz(km)] = make_double2(E.x - O.y, -(E.y + O.x));
+    }
+}
+
+template <int LN>
+WF_HD double2 inverse_pair(const double2* Z, int m) {
+    typedef Geo<LN> G;
+    const double sc = 1.0 / (double)G::M;
+    const double2 z = Z[swz(G::rev(m))];
+    return make_double2(z.x * sc, -z.y * sc);
+}
+
 }  // namespace ws_wf

@@ -263,6 +263,18 @@ WAVESPEC_API int32_t wavespec_fft_real_inverse_batch_host(const double* in_spec,
 WAVESPEC_API int32_t wavespec_fft_real_inverse_batch_device(const double* d_spec, int32_t window_len,
                                                             int64_t n_windows, double* d_out, void* stream);
 
+/* Inverse-FFT wave reconstruction of the selected cycles (north star; BASELINE config 4): the
+ * inverse transform of each window's spectrum masked to its top_k selected bins (bins plane of the
+ * pipeline, -1 = absent; the conjugate half is implied) -> n_windows * window_len samples, i.e. the
+ * sum of the selected cycles over the whole window.  Its last sample equals the sum of the A8b
+ * contributions (Legacy/WaveSpecZZ_1.0.4-kalman.mq5:182-192) of the window. */
+WAVESPEC_API int32_t wavespec_reconstruct_topk_host(const double* spectra, const int32_t* bins,
+                                                    int32_t window_len, int32_t top_k, int32_t n_windows,
+                                                    double* out);
+WAVESPEC_API int32_t wavespec_reconstruct_topk_device(const double* d_spectra, const int32_t* d_bins,
+                                                      int32_t window_len, int32_t top_k, int64_t n_windows,
+                                                      double* d_out, void* stream);
+
 /* Sliding variant of gpu_fft_real_forward_batch (hop-spaced overlapping windows of one host
  * series) — named distinctly, as SURVEY.md section 8b requires. */
 WAVESPEC_API int32_t wavespec_fft_real_forward_sliding(const double* series, int32_t series_len,

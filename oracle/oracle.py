@@ -67,6 +67,7 @@ def lib():
     L = C.CDLL(build())
     L.oracle_fft_forward.argtypes = [_dp, C.c_int, _dp, _dp]
     L.oracle_fft_interleaved.argtypes = [_dp, C.c_int, _dp]
+    L.oracle_fft_inverse.argtypes = [_dp, C.c_int, _dp]
     L.oracle_apply_window.argtypes = [_dp, C.c_int, C.c_int]
     L.oracle_detrend_iir.argtypes = [_dp, C.c_int, C.c_double, _dp, _dp]
     L.oracle_mean_hann.argtypes = [_dp, C.c_int, _dp]
@@ -121,6 +122,14 @@ def fft_forward(x):
 def fft_interleaved(x):
     x = _f64(x); out = np.empty(x.size)
     lib().oracle_fft_interleaved(x, x.size, out)
+    return out
+
+
+def fft_inverse(spec):
+    """n/2 interleaved bins -> n real samples (1/n normalised, Nyquist taken as 0)."""
+    s = _f64(spec)
+    out = np.empty(s.size)
+    lib().oracle_fft_inverse(s, s.size, out)
     return out
 
 

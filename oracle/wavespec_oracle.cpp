@@ -59,6 +59,49 @@ void oracle_fft_forward(const double* data, int n, double* re, double* im) {
     }
 }
 
+// A8d  inverse of the DLL contract of gpu_fft_real_forward (declared L/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:27,
+// used L/WaveSpecZZ_1.0.4-core.mq5:426).  The reference holds no CPU inverse; this is the textbook
+// identity IFFT(X) = conj(FFT(conj X)) / n run through the SAME butterfly loop as
+// FourierTransformManual (L/WaveSpecZZ_1.0.2.mq5:943-974: bit reversal, twiddle recurrence), applied to
+// the Hermitian extension of the n/2 interleaved bins (Nyquist bin, which the forward contract
+// drops, taken as 0).  The 1/n normalisation is this build's decision (include/wavespec_abi.h).
+void oracle_fft_inverse(const double* spec, int n, double* out) {
+    if (n < 2) { if (n == 1) out[0] = spec[0]; return; }
+    std::vector<double> re(n, 0.0), im(n, 0.0);
+    const int h = n / 2;
+    for (int k = 0; k < h; k++) {
+        const double xr = spec[2 * k], xi = (k == 0) ? 0.0 : spec[2 * k + 1];   // X[0] of a real signal is real
+        re[k] = xr; im[k] = -xi;                                                  // conj X[k]
+        if (k > 0) { re[n - k] = xr; im[n - k] = xi; }                            // conj X[n-k] = conj conj X[k]
+    }
+    for (int i = 1, j = 0; i < n; i++) {
+        int bit = n >> 1;
+        for (; (j & bit) != 0; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+    }
+    for (int len = 2; len <= n; len <<= 1) {
+        double ang = -2 * kPi / len;
+        double wlen_r = std::cos(ang), wlen_i = std::sin(ang);
+        for (int i = 0; i < n; i += len) {
+            double w_r = 1.0, w_i = 0.0;
+            for (int j = 0; j < len / 2; j++) {
+                int a = i + j, b = i + j + len / 2;
+                double t_r = re[b] * w_r - im[b] * w_i;
+                double t_i = re[b] * w_i + im[b] * w_r;
+                re[b] = re[a] - t_r;
+                im[b] = im[a] - t_i;
+                re[a] += t_r;
+                im[a] += t_i;
+                double w_t = w_r;
+                w_r = w_r * wlen_r - w_i * wlen_i;
+                w_i = w_t * wlen_i + w_i * wlen_r;
+            }
+        }
+    }
+    for (int i = 0; i < n; i++) out[i] = re[i] / (double)n;
+}
+
 // A4' L/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:3422-3433 (inverse view: what the DLL must return)
 void oracle_fft_interleaved(const double* data, int n, double* out) {
     std::vector<double> re(n), im(n);

@@ -26,6 +26,10 @@ void oracle_fft_forward(const double* data, int n, double* re, double* im);
 /* A4' what the bridge DLL hands back for the same input (L/...-kalman-fast.mq5:3422-3433):
  * out[2k]=re[k], out[2k+1]=im[k], k<n/2. */
 void oracle_fft_interleaved(const double* data, int n, double* out);
+/* A8d inverse of that contract: n/2 interleaved bins (Nyquist taken as 0) -> n real samples, 1/n
+ * normalised; conj -> FourierTransformManual's butterfly loop -> conj (L/WaveSpecZZ_1.0.2.mq5:943-974;
+ * signature L/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:27, use L/WaveSpecZZ_1.0.4-core.mq5:426). */
+void oracle_fft_inverse(const double* spec, int n, double* out);
 
 /* A3  L/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:1126-1177; type 0 none,1 Hann,2 Hamming,3 Blackman,
  * 4 Bartlett; 5 = Hann as written in L/WaveSpecZZ_gpu_wip.mq5:954. In place. */

@@ -93,6 +93,60 @@ int conflicts(int* gather_worst) {
     return worst;
 }
 
+// inverse transform as ws_inverse.cu runs it: unpack pairs (phase), forward passes (one phase each),
+// digit-reversed read-out
+template <int LN>
+int run_inverse(const double* spec, const unsigned char* keep, double* out) {
+    typedef Geo<LN> G;
+    std::vector<double2> tw(G::N);
+    for (int m = 0; m < G::N; m++) {
+        long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)G::N;
+        tw[m] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+    std::vector<double2> Z(G::M, make_double2(NAN, NAN));
+    auto X = [&](int k) { return (keep && !keep[k]) ? make_double2(0.0, 0.0) : make_double2(spec[2 * k], spec[2 * k + 1]); };
+    for (int lane = 0; lane < 32; lane++)
+        for (int k = lane; k <= G::M / 2; k += 32) {
+            const int km = (G::M - k) & (G::M - 1);
+            double2 xa = X(k);
+            const double2 xb = k == 0 ? make_double2(0.0, 0.0) : X(km);
+            if (k == 0) xa.y = 0.0;
+            inverse_unpack<LN>(k, xa, xb, tw.data(), Z.data());
+        }
+    for (int lane = 0; lane < 32; lane++) dif_pass<LN, G::radix(0), G::stride(0), false>(lane, 0, Z.data(), tw.data());
+    if constexpr (G::P > 1) for (int lane = 0; lane < 32; lane++) dif_pass<LN, G::radix(1), G::stride(1), false>(lane, 0, Z.data(), tw.data());
+    if constexpr (G::P > 2) for (int lane = 0; lane < 32; lane++) dif_pass<LN, G::radix(2), G::stride(2), false>(lane, 0, Z.data(), tw.data());
+    if constexpr (G::P > 3) for (int lane = 0; lane < 32; lane++) dif_pass<LN, G::radix(3), G::stride(3), false>(lane, 0, Z.data(), tw.data());
+    if constexpr (G::P > 4) for (int lane = 0; lane < 32; lane++) dif_pass<LN, G::radix(4), G::stride(4), false>(lane, 0, Z.data(), tw.data());
+    for (int lane = 0; lane < 32; lane++)
+        for (int m = lane; m < G::M; m += 32) {
+            const double2 v = inverse_pair<LN>(Z.data(), m);
+            out[2 * m] = v.x; out[2 * m + 1] = v.y;
+        }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int emu_warp_ifft(const double* spec, int n, const unsigned char* keep, double* out) {
+    switch (n) {
+        case 4: return run_inverse<2>(spec, keep, out);
+        case 8: return run_inverse<3>(spec, keep, out);
+        case 16: return run_inverse<4>(spec, keep, out);
+        case 32: return run_inverse<5>(spec, keep, out);
+        case 64: return run_inverse<6>(spec, keep, out);
+        case 128: return run_inverse<7>(spec, keep, out);
+        case 256: return run_inverse<8>(spec, keep, out);
+        case 512: return run_inverse<9>(spec, keep, out);
+        case 1024: return run_inverse<10>(spec, keep, out);
+        case 2048: return run_inverse<11>(spec, keep, out);
+        case 4096: return run_inverse<12>(spec, keep, out);
+        case 8192: return run_inverse<13>(spec, keep, out);
+        default: return -1;
+    }
+}
+
+namespace {
 }  // namespace
 
 extern "C" int emu_warpfft(const double* v, int N, double* out) {

@@ -16,6 +16,30 @@ pytestmark = pytest.mark.gpu
 
 REL_TOL = 1e-9
 
+# Counts the assertions cannot express (windows excluded by a decision-boundary filter, near ties,
+# observed maxima); printed at the end of the module and written to gpurun_out/parity_report.json.
+REPORT = {}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def parity_report():
+    yield
+    import json
+    print("\nPARITY REPORT " + json.dumps(REPORT, sort_keys=True))
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "parity_report.json"), "w") as f:
+            json.dump(REPORT, f, indent=1, sort_keys=True)
+
+
+def count_near_ties(name, spectra, lo, hi, k):
+    """near ties (k-th vs (k+1)-th in-band power closer than 1e-11 relative) are reported, never hidden
+    (SURVEY.md 7.3 item 3): a flipped selection there would be a rounding artefact, not a bug."""
+    c = near_ties(spectra.reshape(-1, spectra.shape[-1]), lo, hi, k)
+    REPORT["near_ties_" + name] = REPORT.get("near_ties_" + name, 0) + c
+    REPORT["near_tie_windows_checked_" + name] = REPORT.get("near_tie_windows_checked_" + name, 0) + int(np.prod(spectra.shape[:-1]))
+    return c
+
 
 @pytest.fixture(scope="module")
 def br():
@@ -145,16 +169,41 @@ def check_planes(br, got, ref, cfg):
             if f >= g.shape[-1]:                            # older row layouts: a prefix of the 15 fields
                 continue
             assert np.abs(g[..., f] - r[..., f]).max() <= REL_TOL * max(1e-300, np.abs(r[..., f]).max())
-        # phase compared on the circle, eta modulo half a period
+        # Phase and eta are functions of atan2(im, re) of the selected bin, so the 1e-9 bar on the
+        # spectrum (max |dX| / max |X| per window) propagates as |d phase| <= 1e-9 * max|X| / |X_k|:
+        # that is the tolerance when the spectra plane is there to give max|X| (the in-band
+        # bins of a raw price window sit 3-5 decades below its DC term); 1e-7 absolute otherwise.
         if g.shape[-1] > 3:
-            dph = np.angle(np.exp(1j * (g[..., 3] - r[..., 3])))
-            assert np.abs(dph).max() < 1e-7
-        m = min(cfg.row_stride, 15)
-        if m > 4:
-            half = 0.5 * np.where(r[..., 2] > 0, r[..., 2], 1.0)
-            d = np.abs(g[..., 4] - r[..., 4])
-            d = np.minimum(d, np.abs(half - d))
-            assert d.max() < 1e-5
+            dph = np.abs(np.angle(np.exp(1j * (g[..., 3] - r[..., 3]))))
+            if "spectra" in ref:
+                xmax = np.abs(ref["spectra"]).max(axis=-1)[..., None]
+                xk = r[..., 0] * n / 2.0
+                tol = REL_TOL * xmax / np.where(xk > 0, xk, np.inf)
+                tol = np.where(xk > 0, np.maximum(tol, 4e-16), 0.0)
+            else:
+                tol = np.full(dph.shape, 1e-7)
+            assert np.all(dph <= tol), float((dph - tol).max())
+            REPORT.setdefault("max_row_phase_err", 0.0)
+            REPORT["max_row_phase_err"] = max(REPORT["max_row_phase_err"], float(dph.max()))
+            m = min(cfg.row_stride, 15)
+            if m > 4:
+                # eta_bars = d / (2 pi f), d in [0, pi): error = phase error * period / 2 pi, except
+                # where d sits on its wrap (0 <-> pi), i.e. within the phase error of a half-period
+                # jump: those rows are compared modulo half a period and COUNTED
+                period = np.where(r[..., 2] > 0, r[..., 2], 1.0)
+                etol = tol * period / (2 * np.pi) + 1e-15 * period
+                d = np.abs(g[..., 4] - r[..., 4])
+                wrapped = d > etol
+                d = np.where(wrapped, np.abs(0.5 * period - d), d)
+                assert np.all(d <= etol), float((d - etol).max())
+                REPORT["eta_rows_on_the_half_period_wrap"] = REPORT.get("eta_rows_on_the_half_period_wrap", 0) + int(wrapped.sum())
+                REPORT["eta_rows_compared"] = REPORT.get("eta_rows_compared", 0) + int(wrapped.size)
+                if m > 5:
+                    # eta_seconds = eta_bars * sample_rate_seconds, same rows, same rule
+                    rate = cfg.sample_rate_seconds
+                    ds = np.abs(g[..., 5] - r[..., 5])
+                    ds = np.where(wrapped, np.abs(0.5 * period * rate - ds), ds)
+                    assert np.all(ds <= etol * rate * (1 + 1e-12)), float((ds - etol * rate).max())
     if "kalman" in ref:
         assert np.array_equal(got["kalman"], ref["kalman"]), "Kalman4D must be bit-identical"
     if "wkalman" in ref:
@@ -165,6 +214,24 @@ def check_planes(br, got, ref, cfg):
         assert np.abs(dph).max() < 1e-6
 
 
+def check_unwrap_and_group_delay(name, gp, rp, tol=1e-6, utol=None, gtol=None):
+    """Unwrapped phase and group delay (A6).  The unwrap adds +-2 pi where a phase step crosses +-pi:
+    a window with a step within `tol` of that decision can legitimately take the other branch, so
+    its planes are compared modulo the branch (unwrapped phase modulo 2 pi) and the window is COUNTED;
+    every other window is compared directly."""
+    ph = rp[:, 0]
+    d = np.abs(np.abs(np.diff(ph, axis=1)) - np.pi)
+    safe = d.min(axis=1) > tol
+    REPORT["unwrap_windows_" + name] = REPORT.get("unwrap_windows_" + name, 0) + int(safe.size)
+    REPORT["unwrap_windows_on_a_pi_decision_" + name] = REPORT.get("unwrap_windows_on_a_pi_decision_" + name, 0) + int((~safe).sum())
+    assert safe.sum() > 0.9 * safe.size
+    assert np.abs(gp[safe, 1] - rp[safe, 1]).max() < (tol if utol is None else utol)
+    assert np.abs(gp[safe, 2] - rp[safe, 2]).max() < (tol if gtol is None else gtol)
+    if (~safe).any():
+        dd = np.angle(np.exp(1j * (gp[~safe, 1] - rp[~safe, 1])))
+        assert np.abs(dd).max() < tol
+
+
 def test_config1_mean_hann_top5(br, oracle):
     """C1: N=512, mean removal + Hann (gpu_wip form), top-5, band 9-200."""
     s = synth.random_walk(0, 4000)
@@ -173,7 +240,7 @@ def test_config1_mean_hann_top5(br, oracle):
     out = br.OUT_SPECTRA | br.OUT_BINS | br.OUT_ROWS | br.OUT_WAVES
     got, ref = run_both(br, oracle, s, cfg, out)
     check_planes(br, got, ref, cfg)
-    assert near_ties(ref["spectra"], 3, 56, 5) == 0
+    assert count_near_ties("config1", ref["spectra"], 3, 56, 5) == 0
 
 
 def test_config2_plain_top8(br, oracle):
@@ -188,6 +255,7 @@ def test_config2_plain_top8(br, oracle):
         # per-bin check off DC: relative to the in-band magnitudes, not the DC term
         gb = got["spectra"][i][:, 12:114]; rb = ref["spectra"][:, 12:114]
         assert rel_err(gb, rb) < REL_TOL
+        count_near_ties("config2", ref["spectra"], 6, 56, 8)
 
 
 def test_config3_iir_blackman_kalman(br, oracle):
@@ -200,6 +268,7 @@ def test_config3_iir_blackman_kalman(br, oracle):
     check_planes(br, got, ref, cfg)
     gb = got["spectra"][:, 80:228]; rb = ref["spectra"][:, 80:228]     # the band itself
     assert rel_err(gb, rb) < REL_TOL
+    count_near_ties("config3", ref["spectra"], 40, 113, 8)
 
 
 def test_config4_phase_and_top8_reconstruction(br, oracle):
@@ -212,12 +281,8 @@ def test_config4_phase_and_top8_reconstruction(br, oracle):
     got, ref = run_both(br, oracle, s, cfg, out)
     check_planes(br, got, ref, cfg)
     # unwrapped phase / group delay only where no bin sits within 1e-6 of a +-pi jump decision
-    ph = ref["phase"][:, 0]
-    d = np.abs(np.abs(np.diff(ph, axis=1)) - np.pi)
-    safe = d.min(axis=1) > 1e-6
-    assert safe.sum() > 0.9 * safe.size
-    assert np.abs(got["phase"][safe, 1] - ref["phase"][safe, 1]).max() < 1e-6
-    assert np.abs(got["phase"][safe, 2] - ref["phase"][safe, 2]).max() < 1e-6
+    count_near_ties("config4", ref["spectra"], 4, 85, 8)
+    check_unwrap_and_group_delay("config4", got["phase"], ref["phase"])
 
 
 def test_config5_n4096_batch_api(br, oracle):
@@ -668,7 +733,8 @@ def test_pla_long_windows_direct_render_fallback(br, oracle):
 
 # ---- warp-per-window FFT kernel (ws_window_fft_warp.cu): N = 512 / 1024 / 2048 -------------------
 @pytest.mark.parametrize("n", [512, 1024, 2048])
-@pytest.mark.parametrize("detrend,wtype", [(0, 3), (1, 3), (2, 1), (2, 0), (1, 0), (0, 5)])
+@pytest.mark.parametrize("detrend,wtype", [(0, 3), (1, 3), (2, 1), (2, 0), (1, 0), (0, 5), (0, 2), (1, 2), (0, 4), (2, 4),
+                                           (1, 4), (2, 2)])
 def test_warp_kernel_prologues_match_oracle(br, oracle, n, detrend, wtype):
     """Every detrend / window combination through the one-warp-per-window kernel, on a window count
     that leaves a ragged last tile and warps without a window in it."""
@@ -855,17 +921,24 @@ def test_config1_full_size_all_windows_against_oracle(br, oracle):
 
 
 # ---- A6 behind the FFT kernels (ws_phase.cu) ----------------------------------------------------
-def _check_phase_planes(got, ref):
+def _check_phase_planes(got, ref, name="phase"):
+    """phase = atan2(im, re) per bin: the 1e-9 bar on the spectrum propagates to
+    |d phase_k| <= 1e-9 * max|X| / |X_k| (bins far below the window's largest are ill-conditioned by
+    exactly that ratio); with no spectra plane at hand the flat 1e-6 of round 1 is kept.  Unwrapped
+    phase and group delay: see check_unwrap_and_group_delay (windows on a +-pi decision are counted
+    and compared modulo 2 pi)."""
     gp, rp = got["phase"], ref["phase"]
-    dph = np.angle(np.exp(1j * (gp[:, 0] - rp[:, 0])))
-    assert np.abs(dph).max() < 1e-6
-    # unwrapped phase / group delay only where no step sits within 1e-6 of a +-pi jump decision
-    ph = rp[:, 0]
-    d = np.abs(np.abs(np.diff(ph, axis=1)) - np.pi)
-    safe = d.min(axis=1) > 1e-6
-    assert safe.sum() > 0.9 * safe.size
-    assert np.abs(gp[safe, 1] - rp[safe, 1]).max() < 1e-9 * max(1.0, np.abs(rp[safe, 1]).max())
-    assert np.abs(gp[safe, 2] - rp[safe, 2]).max() < 1e-9 * 100.0
+    dph = np.abs(np.angle(np.exp(1j * (gp[:, 0] - rp[:, 0]))))
+    if "spectra" in ref:
+        sp = ref["spectra"]
+        mag = np.hypot(sp[:, 0::2], sp[:, 1::2])
+        tol = REL_TOL * mag.max(axis=1, keepdims=True) / np.where(mag > 0, mag, np.inf)
+        tol = np.where(mag > 0, np.maximum(tol, 1e-15), np.pi)      # a bin that is exactly 0 has no phase
+        assert np.all(dph <= tol), float((dph - tol).max())
+    else:
+        assert dph.max() < 1e-6
+    REPORT["max_phase_plane_err_" + name] = max(REPORT.get("max_phase_plane_err_" + name, 0.0), float(dph.max()))
+    check_unwrap_and_group_delay(name, gp, rp, utol=1e-9 * max(1.0, np.abs(rp[:, 1]).max()), gtol=1e-7)
 
 
 @pytest.mark.parametrize("with_spectra", [True, False])

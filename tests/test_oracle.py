@@ -385,3 +385,27 @@ def test_applied_price_matches_the_reference_expressions(oracle):
     assert not np.array_equal(oracle.applied_price(None, h, l, c, 6), h / 3.0 + l / 3.0 + c / 3.0)
     with pytest.raises(ValueError):
         oracle.applied_price(o, h, l, c, 9)
+
+
+# ---- A8d: inverse of the gpu_fft_real_forward contract ------------------------------------------
+@pytest.mark.parametrize("n", [4, 16, 256, 1024, 4096])
+def test_fft_inverse_known_answers(oracle, n):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n)
+    spec = oracle.fft_interleaved(x)
+    back = oracle.fft_inverse(spec)
+    # the forward contract drops the Nyquist bin: the round trip loses exactly that component
+    nyq = np.sum(x * (-1.0) ** np.arange(n))
+    assert np.abs(back - (x - nyq * (-1.0) ** np.arange(n) / n)).max() < 1e-12
+    # independent restatement: numpy's irfft of the same half spectrum with a zero Nyquist bin
+    half = np.zeros(n // 2 + 1, dtype=complex)
+    half[:n // 2] = spec[0::2] + 1j * spec[1::2]
+    half[0] = half[0].real
+    assert np.abs(back - np.fft.irfft(half, n)).max() < 1e-12
+    # a single cosine bin comes back as that cosine with amplitude 2/n per unit of |X|
+    k = n // 4 - 1 if n > 4 else 1
+    one = np.zeros(n)
+    one[2 * k] = 3.0; one[2 * k + 1] = -4.0
+    t = np.arange(n)
+    expect = (2.0 / n) * (3.0 * np.cos(2 * np.pi * k * t / n) + 4.0 * np.sin(2 * np.pi * k * t / n))
+    assert np.abs(oracle.fft_inverse(one) - expect).max() < 1e-13

@@ -25,6 +25,8 @@ def emu():
     dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
     L.emu_warpfft.argtypes = [dp, C.c_int, dp]
     L.emu_warpfft.restype = C.c_int
+    L.emu_warp_ifft.argtypes = [dp, C.c_int, C.c_void_p, dp]
+    L.emu_warp_ifft.restype = C.c_int
     L.emu_warpfft_conflicts.argtypes = [C.c_int, C.POINTER(C.c_int)]
     L.emu_warpfft_conflicts.restype = C.c_int
     return L
@@ -50,3 +52,32 @@ def test_swizzle_keeps_quarter_warps_conflict_free(emu, n):
     assert worst == 1, "a pass access has two lanes of a quarter warp in one 16-byte bank group"
     # the mirrored side of the gather (bin M-k) breaks the digit pattern at k = 0 mod 8 only
     assert g.value <= 2
+
+
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+def test_emulated_warp_inverse_matches_oracle(emu, oracle, n):
+    """The inverse kernel's arithmetic (ws_inverse.cu) against oracle_fft_inverse, and as the inverse
+    of the forward contract: inverse(forward(x)) = x minus the dropped Nyquist component."""
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n)
+    spec = oracle.fft_interleaved(x)
+    out = np.full(n, np.nan)
+    assert emu.emu_warp_ifft(spec, n, None, out) == 0
+    ref = oracle.fft_inverse(spec)
+    assert np.abs(out - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+    nyq = np.sum(x * (-1.0) ** np.arange(n))
+    assert np.abs(out - (x - nyq * (-1.0) ** np.arange(n) / n)).max() < 1e-12
+    if n >= 64:
+        # spectrum masked to a few bins (top-K reconstruction): sum of those cycles over the window
+        keep = np.zeros(n // 2, dtype=np.uint8)
+        sel = rng.choice(np.arange(1, n // 2), size=5, replace=False)
+        keep[sel] = 1
+        assert emu.emu_warp_ifft(spec, n, keep.ctypes.data, out) == 0
+        masked = spec.copy().reshape(-1, 2)
+        masked[keep == 0] = 0.0
+        ref = oracle.fft_inverse(masked.reshape(-1))
+        assert np.abs(out - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+        t = np.arange(n)
+        direct = sum((2.0 / n) * (spec[2 * k] * np.cos(2 * np.pi * k * t / n) - spec[2 * k + 1] * np.sin(2 * np.pi * k * t / n))
+                     for k in sel)
+        assert np.abs(out - direct).max() < 1e-11 * max(1.0, np.abs(direct).max())
