@@ -34,13 +34,15 @@ Job::~Job() {
     if (!dev) return;
     DeviceGuard guard(dev->index);
     if (copied) { cudaEventSynchronize(copied); cudaEventDestroy(copied); }   // nothing may land in a freed caller buffer
-    for (auto& c : chunks) if (c.done) cudaEventDestroy(c.done);
-    if (h2d_done) cudaEventDestroy(h2d_done);
     if (h_rows) {
-        // the pinned rows of a single-window job are written by a copy on `st`
+        // the pinned rows of a single-window job are written by a copy on `st`: wait for it before the
+        // buffer goes back to the pool
         if (state.load() == kLaunched && !chunks.empty() && chunks.back().done) cudaEventSynchronize(chunks.back().done);
+        else cudaStreamSynchronize(st);
         dev->pinned.put(h_rows, h_rows_bytes);
     }
+    for (auto& c : chunks) if (c.done) cudaEventDestroy(c.done);
+    if (h2d_done) cudaEventDestroy(h2d_done);
     d_series.release(); d_rows.release(); d_record.release();
     cudaGetLastError();
 }
