@@ -406,7 +406,7 @@ def main():
 
     for _ in range(args.warmup):
         step()
-    assert bridge.last_kernel() in ("sliding_shared", "sliding_overlap"), bridge.last_kernel()
+    assert bridge.last_kernel() in ("sliding_shared", "sliding_overlap", "sliding_staged"), bridge.last_kernel()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)

@@ -25,6 +25,7 @@
 // FP64 pipe limit, so the kernel is bound by the spectrum store.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "ws_common.cuh"
 #include "ws_epilogue.cuh"
@@ -52,6 +53,10 @@ struct SlideLayout {
     int Lg;             // lanes per window of the batched warp epilogue
     int overlap;        // 1: producer/consumer kernel (selection runs beside the top pass)
     int stage_off;      // overlap: consumer warps' row staging (outside the live work area)
+    int staged;         // 1: spectra rows collected in a shared-memory ring and drained by bulk async stores
+    int ring_off;       // staged: S rings of `ring_slots` spectrum rows (N/2 double2 each)
+    int ring_slots;
+    int special_off;    // staged: [T][8] bins of the packed slot 0 (multiples of N/16)
     int total_bytes;
 };
 
@@ -284,7 +289,216 @@ sliding_overlap_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     }
 }
 
+// ---- staged form: spectra rows leave through the TMA engine -----------------------------------------
+// Measured on this B200 (profiles/r02_stream_bw.json): a pure write stream reaches 6.3-6.9 TB/s, and
+// ONE thread per SM issuing 8 KB bulk async stores from shared memory already reaches 6.4 TB/s, while
+// the chains of the kernel above stop at 5.5 TB/s: their st.global keep the data registers busy until
+// the memory system has taken the data (long-scoreboard stalls 5.4 warps per issue), so compute and
+// store issue serialise inside each of the few chain warps.  Here the chains write their eight bins
+// per window into a shared-memory row instead (st.shared never waits for HBM); when the 64 threads of
+// a segment have completed a row, one of them hands it to the bulk-copy engine
+// (cp.async.bulk.global.shared::cta, 8 KB per row) and the chains go on with the next window while the
+// row drains.  A ring of RING rows per segment decouples the two; the only wait is the issuer's
+// wait_group.read before a slot is rewritten.
+//
+// Thread map: 64 threads per segment, thread kk of a segment owns chain slot k = kk (kk = 0 has no
+// chain: it issues the bulk stores); threads kk < 8 also drop the window's packed-slot bins (computed
+// for the whole tile before the split) into the row.  Consumers as in sliding_overlap_kernel.
+template <int N, int RING>
+struct StageSink {
+    static constexpr int Q = N >> 4, N2 = N / 2;
+    double2* ring;              // this segment's ring
+    double2* g;                 // spectra row of the tile's first window (global)
+    double2* xb;                // band capture of the tile's first window (shared)
+    const double2* special;     // [T][8]
+    int lo, hi, band, nvalid, bar_id, kk;
+    int k;
+    unsigned inband;
+    double2 *spP, *spM, *xpP, *xpM;
+    template <int J> __device__ __forceinline__ void mark() {
+        const int idx = ws_slide::SlotOfs<J>::c * Q + ws_slide::SlotOfs<J>::sgn * k;
+        if (idx >= lo && idx <= hi) inband |= 1u << J;
+    }
+    __device__ __forceinline__ void bind(int k_) {
+        k = k_;
+        inband = 0;
+        mark<0>(); mark<1>(); mark<2>(); mark<3>(); mark<4>(); mark<5>(); mark<6>(); mark<7>();
+    }
+    __device__ __forceinline__ void begin(int m) {
+        double2* slot = ring + (m & (RING - 1)) * N2;
+        spP = slot + k; spM = slot - k;
+        xpP = xb + (m * band - lo) + k; xpM = xb + (m * band - lo) - k;
+    }
+    template <int J> __device__ __forceinline__ void put(double2 v) {
+        constexpr int c = ws_slide::SlotOfs<J>::c * Q;
+        constexpr bool plus = ws_slide::SlotOfs<J>::sgn > 0;
+        (plus ? spP : spM)[c] = v;
+        if ((inband >> J) & 1u) (plus ? xpP : xpM)[c] = v;
+    }
+    // after every window, all 64 threads of the segment
+    __device__ __forceinline__ void end(int m) {
+        double2* slot = ring + (m & (RING - 1)) * N2;
+        if (kk < 8) slot[kk * Q] = special[m * 8 + kk];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // my row bytes -> visible to the copy engine
+        // the slot the NEXT window writes was last read by row m + 1 - RING: at most RING - 2 of the
+        // rows committed so far (.. m - 1) may still be draining when the segment passes the barrier
+        if (kk == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(RING - 2) : "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        if (kk == 0 && m < nvalid) {
+            const unsigned src = (unsigned)__cvta_generic_to_shared(slot);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(g + (int64_t)m * N2), "r"(src), "n"(N2 * 16) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+};
+
+// fills the [T][8] table of packed-slot bins and captures the in-band ones
+template <int N>
+struct SpecialSink {
+    static constexpr int Q = N >> 4;
+    double2* table; double2* xb; int lo, hi, band;
+    __device__ __forceinline__ void put0(int m, int i, double2 v) {
+        if (i == 0) v.y = 0.0;                       // slot 0 carries the Nyquist bin in .y: the contract drops it
+        table[m * 8 + i / Q] = v;
+        if (i >= lo && i <= hi) xb[m * band + (i - lo)] = v;
+    }
+};
+
+template <int N, int RING>
+__global__ void __launch_bounds__(kSlideThreads, 2)
+sliding_staged_kernel(const Params p, const Plan pl, const SlideLayout lay) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* x = reinterpret_cast<double*>(smem_raw);
+    double2* arena = reinterpret_cast<double2*>(smem_raw + lay.arena_off);
+    const int tid = threadIdx.x;
+    const int s = blockIdx.y;
+    const int64_t w0 = p.win_offset + (int64_t)blockIdx.x * pl.T;
+    const int64_t wend = p.win_offset + p.chunk_nwin;
+    const double* src = p.series + (int64_t)s * p.series_stride;
+    const int nvalid = (int)((wend - w0) < pl.T ? (wend - w0) : pl.T);
+
+    for (int i = tid; i < pl.x_len; i += kSlideThreads) {
+        int64_t a = w0 + i;
+        x[i] = (a < p.series_len) ? src[a] : 0.0;
+    }
+    __syncthreads();
+    ws_slide::bottom_level(tid, kSlideThreads, x, pl, p.tw, arena);
+    __syncthreads();
+    for (int i = pl.nst; i >= 2; i--) {
+        ws_slide::SmemSink sink{arena + pl.off[i - 1], pl.stride[i - 1]};
+        ws_slide::direct_pass(tid, kSlideThreads, arena + pl.off[i], pl.stride[i], pl.Q[i], 1 << pl.lev[i - 1],
+                              pl.P[i - 1], p.tw, pl.N, pl.lev[i - 1], sink);
+        __syncthreads();
+    }
+    const double2* lvl3 = arena + pl.off[1];
+    double2* xb = reinterpret_cast<double2*>(smem_raw + lay.xb_off);
+    double2* special = reinterpret_cast<double2*>(smem_raw + lay.special_off);
+    {
+        // packed-slot bins of every window of the tile (8 per window), one window per thread
+        SpecialSink<N> sp{special, xb, p.band_lo, p.band_hi, lay.band};
+        ws_slide::special_pass<N>(tid, kSlideThreads, lvl3, pl.T, p.tw, sp);
+    }
+    __syncthreads();
+
+    const int per = pl.T / pl.S;                 // windows per chain, a multiple of 4
+    const int iters = per >> 2;
+    const int nprod = pl.S * 64;                 // 64 threads per segment
+    const int bar_count = nprod + pl.S * 32;     // an iteration is awaited by one consumer warp per segment
+
+    if (tid < nprod) {
+        const int sub = tid >> 6, kk = tid & 63;
+        StageSink<N, RING> top;
+        top.ring = reinterpret_cast<double2*>(smem_raw + lay.ring_off) + (size_t)sub * RING * (N / 2);
+        top.g = reinterpret_cast<double2*>(p.spectra) + ((int64_t)s * p.spec_nwin + (w0 - p.spec_w0)) * (N / 2);
+        top.xb = xb; top.special = special;
+        top.lo = p.band_lo; top.hi = p.band_hi; top.band = lay.band; top.nvalid = nvalid;
+        top.bar_id = 14 - sub; top.kk = kk;
+        ws_slide::chain_single_stepwise<N>(kk != 0, kk != 0 ? kk : 1, sub * per, per, lvl3, p.tw, top, [&](int it) {
+            __threadfence_block();               // the group's captured bins before the arrival
+            __syncwarp();
+            named_arrive(1 + it, bar_count);
+        });
+        // the rows still draining read this CTA's shared memory
+        if (kk == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        return;
+    }
+
+    const int ncons = kSlideThreads - nprod;
+    const int ctid = tid - nprod;
+    const int cw = ctid >> 5, ncw = ncons >> 5;
+    const int64_t gw_tile = (int64_t)s * p.nwin + w0;
+    double* stage = reinterpret_cast<double*>(smem_raw + lay.stage_off) + cw * 512;
+    for (int b = cw; b < iters * pl.S; b += ncw) {
+        const int it = b / pl.S, seg = b - it * pl.S;
+        named_sync(1 + it, bar_count);
+        const int b0 = seg * per + 4 * it;
+        if (b0 < nvalid) {
+            const int nb = (nvalid - b0) < 4 ? (nvalid - b0) : 4;
+            warp_select_emit_batch<8>(p, nullptr, xb + b0 * lay.band, lay.band, p.band_lo, 8, nb, gw_tile + b0, stage);
+        }
+    }
+}
+
+
+// Staged (bulk-store) form: insertion rule with the 8-lane network, spectra + selection outputs.
+// Tile: the spectrum ring (S x RING x 8 N bytes... N/2 double2 per row) has to fit beside the level-3
+// array and the band capture with two CTAs per SM, so the tile is shorter than the direct-store one.
+static int staged_ring_slots() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("WAVESPEC_RING"); v = (e && atoi(e) == 4) ? 4 : 2; }
+    return v;
+}
+static bool try_staged_plan(const Params& p, Plan& pl, SlideLayout& lay) {
+    static int want = -1;
+    if (want < 0) { const char* e = getenv("WAVESPEC_STAGED"); want = (e && e[0] == '0') ? 0 : 1; }
+    const bool sel = (p.bins || p.rows || p.waves || p.contrib) && !p.band_buf;
+    if (!want || !sel || !p.spectra || p.select != 0 || p.K > 8) return false;
+    if (p.band_hi < p.band_lo || p.band_hi - p.band_lo + 1 > 64) return false;
+    int T, S = 2;
+    switch (p.N) {
+        case 1024: T = 24; break;
+        default: return false;
+    }
+    if (const char* ov = getenv("WAVESPEC_STAGED_TILE")) {       // tuning hook: "T,S"
+        int t = 0, sc = 0;
+        if (sscanf(ov, "%d,%d", &t, &sc) == 2 && t > 0 && sc > 0) { T = t; S = sc; }
+    }
+    if (S > 2 || !ws_slide::plan_make(pl, p.N, T, S, 3)) return false;
+    const int per = T / S;
+    if (per % 4 || per / 4 > 12) return false;                   // named barriers 1..12, 13 and 14 for the segments
+    const int ring = staged_ring_slots();
+    std::memset(&lay, 0, sizeof lay);
+    lay.band = p.band_hi - p.band_lo + 1;
+    lay.x_doubles = (pl.x_len + 1) & ~1;
+    lay.arena_off = lay.x_doubles * 8;
+    const int below3 = lay.arena_off + pl.off[1] * 16;           // dead once level 3 is complete
+    const int work_end = lay.arena_off + pl.arena_slots * 16;
+    const int ncw = (kSlideThreads - S * 64) / 32;
+    const int stage_bytes = ncw * 512 * 8;
+    const int special_bytes = T * 8 * 16;
+    int tail = (work_end + 127) & ~127;
+    int low = 0;
+    auto place = [&](int bytes) {                                // in the dead region if it fits, else at the tail
+        int off;
+        if (low + bytes <= below3) { off = low; low = (low + bytes + 15) & ~15; }
+        else { off = tail; tail = (tail + bytes + 127) & ~127; }
+        return off;
+    };
+    lay.stage_off = place(stage_bytes);
+    lay.special_off = place(special_bytes);
+    lay.xb_off = tail; tail = (tail + T * lay.band * 16 + 127) & ~127;
+    lay.ring_off = tail; tail += S * ring * (p.N / 2) * 16;
+    lay.ring_slots = ring;
+    lay.epi_mode = 2; lay.Lg = 8; lay.overlap = 1; lay.staged = 1;
+    lay.total_bytes = (tail + 15) & ~15;
+    return lay.total_bytes <= 113 * 1024;                        // two CTAs per SM
+}
+
+
 static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
+    if (try_staged_plan(p, pl, lay)) return true;
+    std::memset(&lay, 0, sizeof lay);
     // Tile shapes measured on B200 (profiles/README.md).  With spectra AND selection outputs the
     // chains of a tile are kept on four warps (S (N/16 - 1) <= 128) so that the producer /
     // consumer kernel can run the selection beside them; a pure spectra writer is HBM bound with
@@ -413,6 +627,30 @@ static cudaError_t launch_overlap(const Params& p, const Plan& pl, const SlideLa
     return cudaGetLastError();
 }
 
+template <int N>
+static cudaError_t launch_staged(const Params& p, const Plan& pl, const SlideLayout& lay, cudaStream_t stream) {
+    if constexpr (N != 1024) return cudaErrorInvalidValue;
+    else {
+    dim3 grid((unsigned)((p.chunk_nwin + pl.T - 1) / pl.T), (unsigned)p.n_series);
+    if (lay.ring_slots == 4) {
+        static unsigned long long attr_seen = 0;
+        if (first_launch_on_device(attr_seen)) {
+            cudaError_t e = cudaFuncSetAttribute(sliding_staged_kernel<N, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+            if (e != cudaSuccess) return e;
+        }
+        sliding_staged_kernel<N, 4><<<grid, kSlideThreads, lay.total_bytes, stream>>>(p, pl, lay);
+    } else {
+        static unsigned long long attr_seen = 0;
+        if (first_launch_on_device(attr_seen)) {
+            cudaError_t e = cudaFuncSetAttribute(sliding_staged_kernel<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+            if (e != cudaSuccess) return e;
+        }
+        sliding_staged_kernel<N, 2><<<grid, kSlideThreads, lay.total_bytes, stream>>>(p, pl, lay);
+    }
+    return cudaGetLastError();
+    }
+}
+
 template <int N, bool SPEC, int CAP>
 static cudaError_t launch_one(const Params& p, const Plan& pl, const SlideLayout& lay, cudaStream_t stream) {
     return pl.top == 3 ? launch_top<N, SPEC, CAP, 3>(p, pl, lay, stream) : launch_top<N, SPEC, CAP, 2>(p, pl, lay, stream);
@@ -426,6 +664,7 @@ static cudaError_t launch_n(const Params& p, const Plan& pl, const SlideLayout& 
         if (spec) return launch_one<N, true, 2>(p, pl, lay, stream);
         return launch_one<N, false, 2>(p, pl, lay, stream);
     }
+    if (sel && lay.staged) return launch_staged<N>(p, pl, lay, stream);
     if (sel && lay.overlap) return spec ? launch_overlap<N, true>(p, pl, lay, stream) : launch_overlap<N, false>(p, pl, lay, stream);
     if (spec && sel) return launch_one<N, true, 1>(p, pl, lay, stream);
     if (spec) return launch_one<N, true, 0>(p, pl, lay, stream);
@@ -436,7 +675,7 @@ static cudaError_t launch_n(const Params& p, const Plan& pl, const SlideLayout& 
 cudaError_t launch_sliding_shared(Params p, cudaStream_t stream, const char** which) {
     Plan pl; SlideLayout lay;
     if (!pick_plan(p, pl, lay)) return cudaErrorInvalidValue;
-    if (which && lay.overlap && !p.band_buf) *which = "sliding_overlap";
+    if (which && lay.overlap && !p.band_buf) *which = lay.staged ? "sliding_staged" : "sliding_overlap";
     p.tile_windows = pl.T;
     switch (p.N) {
         case 256: return launch_n<256>(p, pl, lay, stream);

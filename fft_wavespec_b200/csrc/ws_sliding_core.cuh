@@ -336,6 +336,49 @@ WS_HD void chain_single(bool active, int k, int m0, int per, const double2* in, 
     }
 }
 
+// Same chain with a per-WINDOW hand-over: sink.end(m) runs after every window for every thread of the
+// warp, active or not.  The staged kernel (spectra rows collected in shared memory and drained by
+// bulk async stores) synchronises the warps of a segment there.
+template <int N, class Sink, class Hook>
+WS_HD void chain_single_stepwise(bool active, int k, int m0, int per, const double2* in, const double2* tw,
+                                 Sink& sink, Hook hook) {
+    constexpr int Q = TopGeom<N>::Q;
+    constexpr int stride = TopGeom<N>::stride;
+    const double2 w2 = tw[4 * k];
+    const double2 w1a = tw[2 * k];
+    const double2 w0a = tw[k];
+    const double2 w0c = tw[2 * Q - k];
+    const double2* src = in + k;
+    sink.bind(k);
+    double2 qa, qb, qc, qd;
+    double2 eP, eR, oP, oR;
+    double2 ha[4], hb[4];
+    {
+        const double2 I0 = src[m0 * stride], I1 = src[(m0 + 1) * stride], I2 = src[(m0 + 2) * stride];
+        qa = src[(m0 + 3) * stride]; qb = src[(m0 + 4) * stride];
+        qc = src[(m0 + 5) * stride]; qd = src[(m0 + 6) * stride];
+        double2 zP, zR;
+        bfly(I0, qb, w2, zP, zR);
+        bfly(I1, qc, w2, eP, eR);
+        bfly(I2, qd, w2, oP, oR);
+        bfly(zP, oP, w1a, ha[0], ha[1]);
+        bfly_alt(zR, oR, w1a, ha[2], ha[3]);
+    }
+    const double2* nxt = src + (m0 + 7) * stride;
+    int it = 0;
+    for (int m = m0; m < m0 + per; m += 4, it++) {
+        if (active) chain_step<N>(nxt, qa, eP, eR, ha, hb, w2, w1a, w0a, w0c, m, sink);
+        sink.end(m);
+        if (active) chain_step<N>(nxt, qb, oP, oR, hb, ha, w2, w1a, w0a, w0c, m + 1, sink);
+        sink.end(m + 1);
+        if (active) chain_step<N>(nxt, qc, eP, eR, ha, hb, w2, w1a, w0a, w0c, m + 2, sink);
+        sink.end(m + 2);
+        if (active) chain_step<N>(nxt, qd, oP, oR, hb, ha, w2, w1a, w0a, w0c, m + 3, sink);
+        sink.end(m + 3);
+        hook(it);
+    }
+}
+
 // bins that come from the packed slot 0 of level 3 (multiples of Q): one window per thread
 template <int N, class Sink>
 WS_HD void special_pass(int tid, int nthreads, const double2* in, int T, const double2* tw, Sink& sink) {

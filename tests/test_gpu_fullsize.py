@@ -61,7 +61,7 @@ def test_config2_4x200k_every_window(br, oracle):
     s = synth.random_walk_batch(2000, ns, bars)
     cfg = br.default_cfg(n, top_k=k, min_period=18.0, max_period=200.0)
     got = br.pipeline_host(s, cfg, br.OUT_BINS | br.OUT_ROWS | br.OUT_WAVES | br.OUT_SPECTRA)
-    assert br.last_kernel() == "sliding_overlap"            # the kernel bench.py times
+    assert br.last_kernel() in ("sliding_overlap", "sliding_staged")   # the kernel bench.py times
     done, ref = oracle.pipeline_batch_mt(s, ocfg_from(oracle, cfg), THREADS, want=("bins", "rows", "waves"))
     assert done == ns * (bars - n + 1)
     assert np.array_equal(got["bins"], ref["bins"]), "selected cycle bins differ"

@@ -314,7 +314,7 @@ def test_sliding_shared_kernel_all_lengths_and_ragged_tiles(br, oracle, n):
         cfg = br.default_cfg(n, top_k=8, min_period=9.0, max_period=200.0)
         out = br.OUT_SPECTRA | br.OUT_BINS | br.OUT_ROWS | br.OUT_WAVES
         got = br.pipeline_host(s, cfg, out)
-        assert br.last_kernel() in ("sliding_shared", "sliding_overlap")
+        assert br.last_kernel() in ("sliding_shared", "sliding_overlap", "sliding_staged")
         for i in range(2):
             ref = oracle.pipeline_series(s[i], ocfg_from(oracle, cfg), out)
             check_planes(br, {k: v[i] for k, v in got.items()}, ref, cfg)
@@ -328,7 +328,7 @@ def test_sliding_shared_rows_only_and_sort_rule(br, oracle):
         cfg = br.default_cfg(1024, top_k=8, min_period=12.0, max_period=256.0, select=sel)
         out = br.OUT_BINS | br.OUT_ROWS | br.OUT_WKALMAN
         got, ref = run_both(br, oracle, s, cfg, out)
-        assert br.last_kernel() in ("sliding_shared", "sliding_overlap")
+        assert br.last_kernel() in ("sliding_shared", "sliding_overlap", "sliding_staged")
         check_planes(br, got, ref, cfg)
 
 
@@ -339,7 +339,7 @@ def test_sliding_shared_long_series_spot_checks(br, oracle):
     s = synth.random_walk(220, 200000)
     cfg = br.default_cfg(n, top_k=8, outputs=br.OUT_BINS | br.OUT_SPECTRA)
     got = br.pipeline_host(s, cfg)
-    assert br.last_kernel() in ("sliding_shared", "sliding_overlap")
+    assert br.last_kernel() in ("sliding_shared", "sliding_overlap", "sliding_staged")
     nw = got["bins"].shape[0]
     ocfg = ocfg_from(oracle, cfg)
     for w0 in (0, 31, 32, 12345, nw - 40):
@@ -796,7 +796,7 @@ def test_overlap_kernel_rows_bit_identical_to_phase_kernel_and_repeatable(br, n)
     s = synth.random_walk_batch(1200 + n, 4, 120_000 + n)
     cfg = br.default_cfg(n, top_k=8, min_period=18.0, max_period=200.0)
     both = br.pipeline_host(s, cfg, br.OUT_SPECTRA | br.OUT_ROWS | br.OUT_BINS)
-    assert br.last_kernel() == "sliding_overlap"
+    assert br.last_kernel() in ("sliding_overlap", "sliding_staged")
     rows_only = br.pipeline_host(s, cfg, br.OUT_ROWS | br.OUT_BINS)
     assert br.last_kernel() == "sliding_shared"
     assert np.array_equal(both["bins"], rows_only["bins"])
@@ -950,7 +950,7 @@ def test_phase_chain_behind_the_sliding_kernel(br, oracle, with_spectra, monkeyp
     cfg = br.default_cfg(1024, top_k=8, min_period=18.0, max_period=200.0)
     outs = br.OUT_PHASE | br.OUT_BINS | br.OUT_WAVES | br.OUT_ROWS | (br.OUT_SPECTRA if with_spectra else 0)
     got, ref = run_both(br, oracle, s, cfg, outs)
-    assert br.last_kernel() in ("sliding_shared", "sliding_overlap")
+    assert br.last_kernel() in ("sliding_shared", "sliding_overlap", "sliding_staged")
     check_planes(br, got, ref, cfg)
     _check_phase_planes(got, ref)
 
@@ -994,5 +994,5 @@ def test_sliding_kernels_top_k_and_row_strides(br, oracle, top_k, stride):
     s = synth.random_walk(1650 + top_k, 1024 + 130)
     cfg = br.default_cfg(1024, top_k=top_k, row_stride=stride, min_period=18.0, max_period=200.0)
     got, ref = run_both(br, oracle, s, cfg, br.OUT_SPECTRA | br.OUT_BINS | br.OUT_ROWS | br.OUT_WAVES)
-    assert br.last_kernel() in ("sliding_shared", "sliding_overlap")
+    assert br.last_kernel() in ("sliding_shared", "sliding_overlap", "sliding_staged")
     check_planes(br, got, ref, cfg)

@@ -27,6 +27,8 @@ def emu():
     L.emu_sliding.restype = C.c_int
     L.emu_sliding_top.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp]
     L.emu_sliding_top.restype = C.c_int
+    L.emu_sliding_staged.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, dp]
+    L.emu_sliding_staged.restype = C.c_int
     return L
 
 
@@ -84,3 +86,19 @@ def test_emulated_radix4_top_pass_matches_oracle(emu, oracle, n, t, s):
         off_dc = np.abs(out[:, 2:] - ref[:, 2:]).max(axis=1) / np.abs(ref[:, 2:]).max(axis=1)
         assert off_dc.max() < 1e-12
         assert np.all(out[:, 1] == 0.0)
+
+
+@pytest.mark.parametrize("n,t,s", [(1024, 24, 2), (1024, 16, 2), (1024, 32, 2), (1024, 16, 1), (1024, 48, 2)])
+def test_emulated_staged_rows_match_the_direct_store_kernel(emu, oracle, n, t, s):
+    """sliding_staged_kernel's data path (64 threads per segment, rows collected and stored whole):
+    every bin of every row written exactly once (rc -3 otherwise), and the rows are bit for bit the
+    direct-store kernel's."""
+    for extra in (0, t - 1, 2 * t + 5):
+        x = synth.random_walk(310 + n, n + extra)
+        nw = x.size - n + 1
+        a = np.full((nw, n), np.nan); b = np.full((nw, n), np.nan)
+        assert emu.emu_sliding_staged(x, x.size, n, t, s, a) == 0
+        assert emu.emu_sliding(x, x.size, n, t, s, 256, b) == 0
+        assert np.array_equal(a, b)
+        ref = np.stack([oracle.fft_interleaved(x[w:w + n]) for w in range(nw)])
+        assert (np.abs(a - ref).max(axis=1) / np.abs(ref).max(axis=1)).max() < 1e-12
