@@ -451,7 +451,9 @@ static int staged_ring_slots() {
 }
 static bool try_staged_plan(const Params& p, Plan& pl, SlideLayout& lay) {
     static int want = -1;
-    if (want < 0) { const char* e = getenv("WAVESPEC_STAGED"); want = (e && e[0] == '0') ? 0 : 1; }
+    // measured slower than the direct-store form on B200 (2.68 vs 2.39 ms per 1.2 M windows,
+    // profiles/README.md): opt-in
+    if (want < 0) { const char* e = getenv("WAVESPEC_STAGED"); want = (e && e[0] == '1') ? 1 : 0; }
     const bool sel = (p.bins || p.rows || p.waves || p.contrib) && !p.band_buf;
     if (!want || !sel || !p.spectra || p.select != 0 || p.K > 8) return false;
     if (p.band_hi < p.band_lo || p.band_hi - p.band_lo + 1 > 64) return false;
