@@ -215,6 +215,23 @@ def e2e_pass(bridge, host_np, outs, submit, getter, units_per_job):
     return acc
 
 
+def d2h_ceiling_probe(torch, barrier, reduce_min, reduce_sum, n_bytes=1 << 29, reps=4):
+    """The box's device -> pinned-host ceiling with every rank copying AT THE SAME TIME (the e2e legs are
+    bound by it): per-GPU rate of the slowest rank and the sum over ranks."""
+    d = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+    h = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+    h.copy_(d); torch.cuda.synchronize()
+    barrier()
+    t = time.perf_counter()
+    for _ in range(reps):
+        h.copy_(d, non_blocking=True)
+    torch.cuda.synchronize()
+    rate = reps * n_bytes / (time.perf_counter() - t) / 1e9
+    del d, h
+    return {"per_gpu_min_gb_per_s": reduce_min(rate), "sum_over_gpus_gb_per_s": reduce_sum(rate),
+            "how": f"{reps} x {n_bytes >> 20} MiB cudaMemcpyAsync device -> pinned host per rank, all ranks concurrently, in this run"}
+
+
 def live_path_numbers(bridge, synth):
     """The per-bar calls of the 1.1.0 live loop (WaveSpecZZ_1.1.0-gpuopt.mq5:1249, :1313-1392)."""
     x = synth.random_walk(5, N_WINDOW)
@@ -386,12 +403,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def _reduce(x, op):
         if world > 1:
             t = torch.tensor([x], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=op)
             return float(t.item())
         return x
+
+    def max_over_ranks(x):
+        return _reduce(x, dist.ReduceOp.MAX) if world > 1 else x
 
     def timed(nsteps, **kw):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -487,14 +507,12 @@ def main():
                            bridge.gpu_try_get_cycles_batch, out_doubles, nwin * TOP_K, out_doubles * 8)
         e2e_rows["product"] = "stride-15 rows: top_k x 15 doubles per window (960 B/window), PCIe bound"
         e2e_rows["api"] = "gpu_submit_extract_cycles_batch / gpu_try_get_cycles_batch / gpu_free_job (imports.mqh), pinned host buffers"
-        pcie = os.path.join(ROOT, "profiles", "r02_pcie_ceiling.json")
-        if os.path.exists(pcie):
-            try:
-                ceil = json.load(open(pcie))
-                e2e_rows["d2h_ceiling_gb_per_s_per_gpu"] = ceil.get(str(world), ceil.get("1"))
-                e2e_rows["d2h_ceiling_source"] = "profiles/r02_pcie_ceiling.json (probe_pcie.py, ranks concurrently)"
-            except Exception:
-                pass
+        # both legs are PCIe bound: print the box's concurrent D2H ceiling measured in this run next to them
+        ceiling = d2h_ceiling_probe(torch, barrier, lambda x: _reduce(x, dist.ReduceOp.MIN) if world > 1 else x,
+                                    lambda x: _reduce(x, dist.ReduceOp.SUM) if world > 1 else x)
+        for leg in (e2e, e2e_rows):
+            leg["d2h_ceiling"] = ceiling
+            leg["frac_of_d2h_ceiling"] = leg["d2h_gb_per_s_per_gpu"] / ceiling["per_gpu_min_gb_per_s"]
 
     live = None
     cpu = None

@@ -2,7 +2,7 @@
 //
 // Same job as ws_window_fft.cu (SURVEY.md section 8a rows A2a/A2b/A3 prologues, A4 transform, A5
 // power, A7/A8 selection and rows) for the window lengths of BASELINE.json's configs
-// (N = 512 .. 2048) when the windows come from the series itself (no PLA feed) and the phase
+// (N = 512 .. 4096) when the windows come from the series itself (no PLA feed) and the phase
 // chain is not requested.  The CTA stages a tile of consecutive windows once (and runs the tile-
 // level trend IIR), then its warps take windows round-robin and never meet again: the transform
 // (ws_warpfft_core.cuh) is in place in a warp-private shared array with __syncwarp between
@@ -157,8 +157,9 @@ window_fft_warp_kernel(const Params p, const WarpLayout L) {
 
 static int warp_pick_tile(const Params& p, int kWarps) {
     // 64 windows per tile when the staged samples stay within 4096 + N doubles; strided batches
-    // (hop ~ N) get at least one window per warp while the tile fits 12288 doubles
-    long budget = 4096 + p.N;
+    // (hop ~ N) get at least one window per warp while the tile fits 12288 doubles.  N = 4096 keeps
+    // its tile short: five 32 KB transform arrays leave ~50 KB for the staged samples.
+    long budget = p.N >= 4096 ? 64 + p.N : 4096 + p.N;
     long t = (budget - p.N) / p.hop + 1;
     if (t < kWarps && (long)(kWarps - 1) * p.hop + p.N <= 12288) t = kWarps;
     const long cap = 64 - 64 % kWarps + (64 % kWarps ? kWarps : 0);   // multiple of kWarps: no warp idles on a full tile
@@ -183,7 +184,8 @@ static cudaError_t launch_ln(Params p, cudaStream_t stream) {
 }
 
 // Warps per CTA, measured on B200 (profiles/README.md): 12 warps x 2 CTAs (80 registers) at
-// N = 512, 8 warps x 2 CTAs (128 registers) at N = 1024, 12 warps x 1 CTA at N = 2048.
+// N = 512, 8 warps x 2 CTAs (128 registers) at N = 1024, 12 warps x 1 CTA at N = 2048, 5 warps x 1 CTA
+// at N = 4096 (a warp's transform array is 32 KB there).
 // WAVESPEC_K1W=0 (tuning hook) routes everything to the CTA kernel of ws_window_fft.cu.
 static bool warp_enabled() {
     static int v = -1;
@@ -201,6 +203,7 @@ static bool fits(const Params& p, int W) {
 // 0: not served.  N = 2048 drops to 8 warps when a wide band's powers do not fit beside 12 Z arrays.
 static int warps_for(const Params& p) {
     if (p.N == 1024) return fits(p, 8) ? 8 : 0;
+    if (p.N == 4096) return fits(p, 5) ? 5 : (fits(p, 4) ? 4 : 0);
     if (fits(p, 12)) return 12;
     return p.N == 2048 && fits(p, 8) ? 8 : 0;
 }
@@ -208,7 +211,7 @@ static int warps_for(const Params& p) {
 // true when this kernel serves the request (the caller falls back to ws_window_fft.cu otherwise)
 bool window_fft_warp_supported(const Params& p) {
     if (!warp_enabled() || p.feed || p.phase) return false;
-    if (p.N < 512 || p.N > 2048) return false;    // N = 256: half the lanes idle in the passes, the CTA kernel wins
+    if (p.N < 512 || p.N > 4096) return false;    // N = 256: half the lanes idle in the passes, the CTA kernel wins
     if (p.chunk_nwin < 1) return false;
     return warps_for(p) != 0;
 }
@@ -219,6 +222,7 @@ cudaError_t launch_window_fft_warp(Params p, cudaStream_t stream) {
         case 512:  return launch_ln<9, 12, 2>(p, stream);
         case 1024: return launch_ln<10, 8, 2>(p, stream);
         case 2048: return W == 12 ? launch_ln<11, 12, 1>(p, stream) : launch_ln<11, 8, 1>(p, stream);
+        case 4096: return W == 5 ? launch_ln<12, 5, 1>(p, stream) : launch_ln<12, 4, 1>(p, stream);
         default:   return cudaErrorInvalidValue;
     }
 }

@@ -60,7 +60,14 @@ run("C4 plain: phase+waves+rows", 1024, 4, 100000, PH | W | R, top_k=8, min_peri
 run("C4 plain: spectra+phase+rows", 1024, 4, 100000, S | PH | R, top_k=8, min_period=18.0, max_period=200.0)
 run("C5 N=4096 K=4 rows", 4096, 2, 200000, R, top_k=4, min_period=9.0, max_period=200.0)
 run("C5 N=4096 K=4 spectra+rows", 4096, 2, 200000, S | R, top_k=4, min_period=9.0, max_period=200.0)
+run("N=1024 IIR+Blackman (spectra+bins)", 1024, 4, 100000, S | B, top_k=8, min_period=18.0, max_period=52.0,
+    detrend=br.DETREND_IIR, trend_period=1024.0, window_type=br.WINDOW_BLACKMAN)
+run("N=4096 IIR+Blackman (spectra+bins)", 4096, 2, 100000, S | B, top_k=8, min_period=18.0, max_period=52.0,
+    detrend=br.DETREND_IIR, trend_period=1024.0, window_type=br.WINDOW_BLACKMAN)
+run("N=4096 Hann K=4 band 9-200 (rows)", 4096, 2, 100000, R, top_k=4, min_period=9.0, max_period=200.0,
+    window_type=br.WINDOW_HANN)
 run("PLA feed + FFT", 1024, 1, 30000, S | B, feed=br.FEED_PLA)
+run("PLA feed + FFT (4 x 100k)", 1024, 4, 100000, S | B, feed=br.FEED_PLA)
 TR = br.OUT_TRACKER
 run("C3 tracker slots only", 2048, 16, 200000, TR, min_period=18.0, max_period=52.0, detrend=br.DETREND_IIR,
     trend_period=1024.0, window_type=br.WINDOW_BLACKMAN)

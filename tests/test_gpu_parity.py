@@ -731,8 +731,8 @@ def test_pla_long_windows_direct_render_fallback(br, oracle):
         assert np.array_equal(bounds[w, :m, 0], st_[:m]) and np.array_equal(bounds[w, :m, 1], en_[:m])
 
 
-# ---- warp-per-window FFT kernel (ws_window_fft_warp.cu): N = 512 / 1024 / 2048 -------------------
-@pytest.mark.parametrize("n", [512, 1024, 2048])
+# ---- warp-per-window FFT kernel (ws_window_fft_warp.cu): N = 512 / 1024 / 2048 / 4096 ------------
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096])
 @pytest.mark.parametrize("detrend,wtype", [(0, 3), (1, 3), (2, 1), (2, 0), (1, 0), (0, 5), (0, 2), (1, 2), (0, 4), (2, 4),
                                            (1, 4), (2, 2)])
 def test_warp_kernel_prologues_match_oracle(br, oracle, n, detrend, wtype):
