@@ -43,6 +43,7 @@ struct Params {
     double* phase;             // [n_series][nwin][3][N/2], or nullptr
     double2* band_buf;         // scratch [n_series][chunk_nwin][band]: in-band bins handed from the
                                // sliding kernel to the rows kernel (ws_rows.cu), or nullptr
+    long long* dbg;            // optional [1024][4] clock64 phase stamps of the first CTAs (WAVESPEC_TIMING_FILE), or nullptr
     int32_t tile_windows;      // windows per CTA tile
     int32_t k1_wpc_cap;        // per-window FFT: max windows transformed concurrently by a CTA
 };

@@ -5,8 +5,11 @@
 // kept between calls.  The one exception is the PLA feed, whose recursion-overflow flag has to be
 // read back before the call can report success.
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <tuple>
+#include <vector>
 
 #include "ws_runtime.h"
 
@@ -106,8 +109,19 @@ static int run_tracker_path(Params p, const wavespec_pipeline_cfg* c, int32_t* d
     const bool sel = p.rows || p.bins || p.waves || p.contrib;
     const bool other = sel || p.spectra || p.phase;
     static const bool walk_all = getenv("WAVESPEC_TRACKER_WALK_ALL") != nullptr;      // testing hook
-    int64_t fixed = walk_all ? -1 : tracker_fixed_point(p.N, p.band_lo, p.band_hi, c->tracker_tolerance,
-                                                        c->tracker_max_inactive, 4096);
+    // the fixed point is a pure function of (N, band, tolerance, max_inactive): computed once per shape
+    int64_t fixed = -1;
+    if (!walk_all) {
+        static std::mutex mu;
+        static std::map<std::tuple<int, int, int, double, int>, int64_t> cache;
+        const auto key = std::make_tuple(p.N, p.band_lo, p.band_hi, c->tracker_tolerance, c->tracker_max_inactive);
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it == cache.end())
+            it = cache.emplace(key, tracker_fixed_point(p.N, p.band_lo, p.band_hi, c->tracker_tolerance,
+                                                        c->tracker_max_inactive, 4096)).first;
+        fixed = it->second;
+    }
     // bars the sequential kernel has to walk: one past the fixed point (its slots are final)
     const int64_t walk = (fixed < 0 || fixed + 1 >= nwin) ? nwin : fixed + 1;
     const int64_t need = other ? nwin : walk;                 // windows the FFT kernels must cover
@@ -333,7 +347,24 @@ int run_pipeline(Device& dev, const double* d_series, int32_t n_series, int32_t 
                     which = "sliding_shared";
                 } else {
                     which = "sliding_shared";
-                    WS_CUDA(ws::launch_sliding_shared(p, st, &which), "sliding_shared kernel");
+                    const char* tf = getenv("WAVESPEC_TIMING_FILE");      // debug: phase stamps of the first 1024 CTAs
+                    if (tf && p.spectra && p.rows) {
+                        Params q = p;
+                        DeviceBuf stamps;
+                        WS_CUDA(stamps.alloc(1024 * 4 * 8), "cudaMalloc(stamps)");
+                        WS_CUDA(cudaMemsetAsync(stamps.p, 0, stamps.bytes, st), "cudaMemsetAsync(stamps)");
+                        q.dbg = stamps.as<long long>();
+                        WS_CUDA(ws::launch_sliding_shared(q, st, &which), "sliding_shared kernel");
+                        std::vector<long long> h(1024 * 4);
+                        WS_CUDA(cudaMemcpyAsync(h.data(), stamps.p, stamps.bytes, cudaMemcpyDeviceToHost, st), "D2H stamps");
+                        WS_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize(stamps)");
+                        if (FILE* f = fopen(tf, "w")) {
+                            for (int i = 0; i < 1024; i++) fprintf(f, "%lld %lld %lld %lld\n", h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+                            fclose(f);
+                        }
+                    } else {
+                        WS_CUDA(ws::launch_sliding_shared(p, st, &which), "sliding_shared kernel");
+                    }
                 }
             } else {
                 WS_CUDA(ws::launch_window_fft(p, st, &which), "window_fft kernel");

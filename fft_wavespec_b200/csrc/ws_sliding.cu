@@ -221,6 +221,10 @@ template <int N, bool SPEC>
 __global__ void __launch_bounds__(kSlideThreads, 2)
 sliding_overlap_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // phase stamps of the first CTAs (debug, WAVESPEC_TIMING_FILE): start, lower passes done, last
+    // producer warp done, last consumer warp done
+    long long* dbg = (p.dbg && blockIdx.y == 0 && blockIdx.x < 1024) ? p.dbg + 4 * blockIdx.x : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64();
     double* x = reinterpret_cast<double*>(smem_raw);
     double2* arena = reinterpret_cast<double2*>(smem_raw + lay.arena_off);
     const int tid = threadIdx.x;
@@ -244,6 +248,7 @@ sliding_overlap_kernel(const Params p, const Plan pl, const SlideLayout lay) {
         __syncthreads();
     }
 
+    if (dbg && tid == 0) dbg[1] = clock64();
     TopSink<N, SPEC, 1, 3> top;
     top.g = SPEC ? reinterpret_cast<double2*>(p.spectra) + ((int64_t)s * p.spec_nwin + (w0 - p.spec_w0)) * (N / 2) : nullptr;
     top.xb = reinterpret_cast<double2*>(smem_raw + lay.xb_off);
@@ -265,6 +270,7 @@ sliding_overlap_kernel(const Params p, const Plan pl, const SlideLayout lay) {
             __syncwarp();
             named_arrive(1 + it, bar_count);
         });
+        if (dbg && (tid & 31) == 0) atomicMax((unsigned long long*)&dbg[2], (unsigned long long)clock64());
         return;
     }
 
@@ -287,6 +293,7 @@ sliding_overlap_kernel(const Params p, const Plan pl, const SlideLayout lay) {
             warp_select_emit_batch<8>(p, nullptr, top.xb + b0 * lay.band, lay.band, top.lo, 8, nb, gw_tile + b0, stage);
         }
     }
+    if (dbg && (tid & 31) == 0) atomicMax((unsigned long long*)&dbg[3], (unsigned long long)clock64());
 }
 
 // ---- staged form: spectra rows leave through the TMA engine -----------------------------------------
