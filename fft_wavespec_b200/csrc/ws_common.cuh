@@ -31,6 +31,7 @@ struct Params {
     const double2* tw;         // exp(-2 pi i m / N), m = 0..N-1
     const double* wtab;        // window coefficients w[i], i = 0..N-1 (or nullptr)
     const double* apow;        // iir_alpha^j, j = 0..N-1 (or nullptr)
+    const double2* rowtab;     // per bin k < N/2: (N/k, N/(2 pi k)) for the result rows (or nullptr)
     const double* feed;        // optional pre-built per-window feed [n_series][nwin][N] (PLA), or nullptr
     double* spectra;           // [n_series][spec_nwin][N] interleaved, or nullptr; window w of series s is row
                                // s * spec_nwin + (w - spec_w0)  (spec_nwin = nwin, spec_w0 = 0 for a caller's

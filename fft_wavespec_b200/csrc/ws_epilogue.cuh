@@ -233,7 +233,9 @@ __device__ __forceinline__ void warp_select_emit_batch(const Params& p, double* 
         WS_CE(0, 4) WS_CE(1, 5) WS_CE(2, 6) WS_CE(3, 7)
         WS_CE(2, 4) WS_CE(3, 5)
         WS_CE(1, 2) WS_CE(3, 4) WS_CE(5, 6)
-#pragma unroll
+        // the three merge rounds share one copy of the code (the epilogue runs once per group of
+        // windows: straight-line code this long is fetched from L2 every time)
+#pragma unroll 1
         for (int d = 1; d <= 4; d <<= 1) {
             double pv[8];
             int pe[8];
@@ -330,19 +332,25 @@ __device__ __forceinline__ void warp_select_emit_batch(const Params& p, double* 
 #pragma unroll
         for (int i = 0; i < kRowFields; i++) f[i] = 0.0;
         if (has_row && my_bin > 0) {
-            f[0] = 2.0 * sqrt(my_pow) / (double)N;
-            f[1] = (double)my_bin / (double)N;
-            f[2] = (double)N / (double)my_bin;
+            // N is a power of two: the divisions by N are exact scalings.  The period N/k and the factor
+            // 1/(2 pi freq) come from the per-bin table when the caller provides one (same correctly
+            // rounded period; the eta fields differ from the divided form by an ulp, inside their 1e-9 bar)
+            const double invN = 1.0 / (double)N;
+            f[0] = 2.0 * sqrt(my_pow) * invN;
+            f[1] = (double)my_bin * invN;
+            double bars_per_rad;
+            if (p.rowtab) { const double2 t = __ldg(p.rowtab + my_bin); f[2] = t.x; bars_per_rad = t.y; }
+            else { f[2] = (double)N / (double)my_bin; bars_per_rad = 1.0 / (2.0 * kPi * f[1]); }
             // phase at the newest sample: atan2 + 2 pi k (N-1)/N + pi/2, wrapped to [-pi, pi].
             // 2 pi k (N-1)/N == -2 pi k/N (mod 2 pi); the small angle keeps the wrap to one step.
-            double ph = atan2(im, re) + (0.5 * kPi - 2.0 * kPi * (double)my_bin / (double)N);
+            double ph = atan2(im, re) + (0.5 * kPi - 2.0 * kPi * (double)my_bin * invN);
             if (ph > kPi) ph -= 2.0 * kPi;
             if (ph < -kPi) ph += 2.0 * kPi;
             f[3] = ph;
             double d = 0.5 * kPi - ph;                  // bars to the next extremum of amp*sin
             if (d < 0.0) d += kPi;
             if (d >= kPi) d -= kPi;
-            f[4] = d / (2.0 * kPi * f[1]);
+            f[4] = d * bars_per_rad;
             f[5] = f[4] * p.sample_rate_seconds;
             f[6] = bsum > 0.0 ? my_pow / bsum : 0.0;
         }

@@ -193,6 +193,7 @@ int run_pipeline(Device& dev, const double* d_series, int32_t n_series, int32_t 
     if ((rc = dev.get_twiddles(N, &p.tw))) return rc;
     if ((rc = dev.get_window(N, c->window_type, &p.wtab))) return rc;
     p.has_window = p.wtab != nullptr;
+    if (out.rows && (rc = dev.get_rowtab(N, &p.rowtab))) return rc;
     if (c->detrend == WAVESPEC_DETREND_IIR) {
         // Legacy/...-kalman-fast.mq5:3367-3369
         double omega = 2.0 * kPi / c->trend_period;
@@ -230,7 +231,9 @@ int run_pipeline(Device& dev, const double* d_series, int32_t n_series, int32_t 
     if (c->feed == WAVESPEC_FEED_PLA) {
         // PLA lines are window-private (the recursion restarts per window): build them chunk by
         // chunk into a bounded temporary and feed the per-window FFT kernel from it.
-        const size_t budget = (size_t)1 << 30;   // bytes of feed per chunk
+        // bytes of feed per chunk: a PLA thread owns one window for a long walk, so a launch needs
+        // several hundred thousand windows to fill the device (180 GB of HBM: 8 GB is cheap)
+        const size_t budget = (size_t)8 << 30;
         int64_t chunk = (int64_t)(budget / ((size_t)n_series * N * 8));
         if (chunk < 1) chunk = 1;
         if (chunk > w_count) chunk = w_count;

@@ -58,15 +58,25 @@ pla_kernel(const double* __restrict__ series, int64_t series_stride, int64_t nwi
         const int len = fit ? e - s + 1 : 0;
         const int len_max = __reduce_max_sync(kFull, len);
 
-        // FitPlaSegment (:387-417): sums in ascending index order
-        double sx = 0.0, sy = 0.0, sx2 = 0.0, sxy = 0.0;
-        for (int t = 0; t < len_max; ++t) {
-            if (t < len) {
-                const int i = s + t;
-                const double x = (double)i, v = y[i];
-                sx += x; sy += v; sx2 += x * x; sxy += x * v;
+        // FitPlaSegment (:387-417).  sy and sxy are accumulated in ascending index order exactly as the
+        // reference does.  sx = sum i and sx2 = sum i*i are sums of integers far below 2^53: every
+        // partial sum of the reference's loop is exact, so the closed forms below are bit-identical to
+        // it.  x runs as a double incremented by 1.0 (exact) instead of a conversion per sample.
+        double sy = 0.0, sxy = 0.0;
+        {
+            double x = (double)s;
+            for (int t = 0; t < len_max; ++t) {
+                if (t < len) {
+                    const double v = y[s + t];
+                    sy += v; sxy += x * v;
+                    x += 1.0;
+                }
             }
         }
+        const long long ls = s, le = e, ln = len;
+        const double sx = (double)((ls + le) * ln / 2);
+        auto sq = [](long long n) { return n * (n + 1) * (2 * n + 1) / 6; };          // sum_{i=0}^{n} i^2
+        const double sx2 = (double)(sq(le) - (ls > 0 ? sq(ls - 1) : 0));
         double slope = 0.0, icpt = 0.0;
         bool leaf = on && e >= s;                       // AppendPlaSegment ignores end < start
         if (on && s == e) icpt = y[s];
@@ -81,12 +91,15 @@ pla_kernel(const double* __restrict__ series, int64_t series_stride, int64_t nwi
         // ComputePlaSegmentError (:419-440)
         double mx = 0.0;
         int worst = s;
-        for (int t = 0; t < len_max; ++t) {
-            if (t < len) {
-                const int i = s + t;
-                const double approx = slope * (double)i + icpt;
-                const double err = fabs(y[i] - approx);
-                if (err > mx) { mx = err; worst = i; }
+        {
+            double x = (double)s;
+            for (int t = 0; t < len_max; ++t) {
+                if (t < len) {
+                    const double approx = slope * x + icpt;
+                    const double err = fabs(y[s + t] - approx);
+                    if (err > mx) { mx = err; worst = s + t; }
+                    x += 1.0;
+                }
             }
         }
         if (fit) {
@@ -112,8 +125,9 @@ pla_kernel(const double* __restrict__ series, int64_t series_stride, int64_t nwi
         }
         if (line_w) {
             const int rmax = __reduce_max_sync(kFull, rlen);
+            double x = (double)s;
             for (int t = 0; t < rmax; ++t)
-                if (t < rlen) line_w[s + t] = slope * (double)(s + t) + icpt;
+                if (t < rlen) { line_w[s + t] = slope * x + icpt; x += 1.0; }
         }
     }
     if (active) {
@@ -130,7 +144,10 @@ cudaError_t launch_pla(const double* series, int64_t series_stride, int32_t n_se
                        int32_t* seg_bounds, int32_t* seg_counts, int32_t bounds_cap, int32_t* overflow,
                        cudaStream_t stream) {
     dim3 grid((unsigned)((nwin + kPlaThreads - 1) / kPlaThreads), (unsigned)n_series);
-    pla_kernel<<<grid, kPlaThreads, 0, stream>>>(series, series_stride, nwin, N, hop, max_segments, max_error,
+    // The walk is bound by the FP64 pipe, which eight warps per scheduler already fill.  An (unused)
+    // dynamic shared-memory request of 27 KB caps the residency at 8 CTAs per SM: a launch then runs
+    // in twice as many waves and its last, partly filled wave costs half as much.
+    pla_kernel<<<grid, kPlaThreads, 27 * 1024, stream>>>(series, series_stride, nwin, N, hop, max_segments, max_error,
                                                  lines, seg_bounds, seg_counts, bounds_cap, overflow);
     return cudaGetLastError();
 }

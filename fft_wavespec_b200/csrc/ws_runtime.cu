@@ -149,6 +149,26 @@ int Device::get_apow(int N, double alpha, const double** out) {
     return WAVESPEC_OK;
 }
 
+// Per-bin constants of the result rows: .x = period N/k (the correctly rounded quotient the row
+// carries), .y = N / (2 pi k) = 1 / (2 pi freq), the factor that turns a phase distance into bars.
+int Device::get_rowtab(int N, const double2** out) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = rowtab.find(N);
+    if (it == rowtab.end()) {
+        std::vector<double> h((size_t)N, 0.0);          // N/2 bins x 2
+        for (int k = 1; k < N / 2; k++) {
+            h[2 * k] = (double)N / (double)k;
+            h[2 * k + 1] = 1.0 / (2.0 * kPi * ((double)k / (double)N));
+        }
+        std::unique_ptr<DeviceBuf> buf;
+        int rc = upload_table(h, buf, "row table");
+        if (rc) return rc;
+        it = rowtab.emplace(N, std::move(buf)).first;
+    }
+    *out = it->second->as<double2>();
+    return WAVESPEC_OK;
+}
+
 // ---- devices -----------------------------------------------------------------------------------
 Device* primary_device() {
     std::lock_guard<std::mutex> lk(g_rt.mu);
@@ -248,7 +268,7 @@ void close_all_devices() {
             if (it->second->dev == d.get()) it = jobs.erase(it); else ++it;
         d->queue.clear();
         d->band_scratch.clear(); d->phase_scratch.clear();
-        d->tw.clear(); d->win.clear(); d->apow.clear();
+        d->tw.clear(); d->win.clear(); d->apow.clear(); d->rowtab.clear();
         d->pinned.trim();
         for (auto s : d->streams) cudaStreamDestroy(s);
         for (auto s : d->copy_streams) cudaStreamDestroy(s);

@@ -108,6 +108,7 @@ struct Device {
     std::map<int, std::unique_ptr<DeviceBuf>> tw;                       // N -> exp(-2 pi i m/N)
     std::map<std::pair<int, int>, std::unique_ptr<DeviceBuf>> win;      // (N, type) -> w[i]
     std::map<std::pair<int, double>, std::unique_ptr<DeviceBuf>> apow;  // (N, alpha) -> alpha^j
+    std::map<int, std::unique_ptr<DeviceBuf>> rowtab;                   // N -> per bin (N/k, N/(2 pi k))
     std::map<cudaStream_t, std::unique_ptr<DeviceBuf>> band_scratch;    // ws_sliding.cu -> ws_rows.cu hand-off
     std::map<cudaStream_t, std::unique_ptr<DeviceBuf>> phase_scratch;   // spectra of a window range (phase path)
     PinnedPool pinned;
@@ -123,6 +124,7 @@ struct Device {
     int get_twiddles(int N, const double2** out);
     int get_window(int N, int type, const double** out);
     int get_apow(int N, double alpha, const double** out);
+    int get_rowtab(int N, const double2** out);
 };
 
 enum JobKind { kJobWindow = 0, kJobBatchRows = 1, kJobCacheRecord = 2 };
