@@ -517,7 +517,10 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
     switch (p.N) {
         case 256:  T = 128; S = (any_sel && p.spectra) ? 4 : 16; break;
         case 512:  T = 64;  S = (any_sel && p.spectra) ? 4 : 8; break;
-        case 1024: T = 32;  S = any_sel ? (p.spectra ? 2 : 4) : 1; break;
+        // spectra + rows: 40 windows per tile (two segments of 20) is what fits two CTAs per SM with
+        // the consumers' row staging in the dead part of the work area; a longer tile spreads the lower
+        // passes and the consumers' tail over more windows (32 -> 40: 2.28 -> 2.13 ms per 1.2 M windows)
+        case 1024: T = (any_sel && p.spectra) ? 40 : 32;  S = any_sel ? (p.spectra ? 2 : 4) : 1; break;
         case 2048: T = 16;  S = 2;  break;
         case 4096: T = 16;  S = (any_sel || p.band_buf) ? 2 : 1; break;
         default: return false;
@@ -586,15 +589,18 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
         if (want && sel && lay.band > 0 && lay.epi_mode == 2 && lay.Lg == 8 && pl.top == 3 && p.N <= 2048 &&
             p.spectra && pl.S * gen <= 128 && pl.S <= (kSlideThreads - ((pl.S * gen + 31) & ~31)) / 32 &&
             per % 4 == 0 && per / 4 <= 14) {
-            // capture and row staging live beside the work area (level 3 is read throughout)
+            // The capture lives beside the work area (level 3 is read throughout).  The consumers' row
+            // staging goes where the samples and the deeper levels were: they are dead once level 3 is
+            // complete, which is before the CTA splits.
             const int xo = (work_end + 15) & ~15;
-            const int so = (xo + xb_bytes + 15) & ~15;
             const int stage_bytes = (kSlideThreads - ((pl.S * gen + 31) & ~31)) / 32 * 512 * 8;   // per consumer warp
-            if (so + stage_bytes <= 113 * 1024) {        // keep two CTAs per SM
+            int so = 0, total = xo + xb_bytes;
+            if (stage_bytes > below3) { so = (xo + xb_bytes + 15) & ~15; total = so + stage_bytes; }
+            if (total <= 113 * 1024) {                   // keep two CTAs per SM
                 lay.overlap = 1;
                 lay.xb_off = xo;
                 lay.stage_off = so;
-                end = so + stage_bytes;
+                end = total;
             }
         }
     }

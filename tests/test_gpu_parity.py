@@ -787,6 +787,19 @@ def test_warp_kernel_many_series_rows_only(br, oracle):
 
 
 # ---- producer / consumer sliding kernel vs the phase-ordered one --------------------------------
+@pytest.mark.parametrize("n,tile", [(1024, 40), (512, 64), (256, 128)])
+def test_overlap_kernel_ragged_tiles_against_oracle(br, oracle, n, tile):
+    """The producer / consumer kernel (spectra + rows, band <= 64 bins) on window counts around its tile
+    length: one window, one short of a tile, exactly one, one more, and two tiles plus a ragged third."""
+    for nwin in (1, tile - 1, tile, tile + 1, 2 * tile + 7):
+        s = synth.random_walk(1300 + n + nwin, n + nwin - 1)
+        cfg = br.default_cfg(n, top_k=8, min_period=18.0 * n / 1024, max_period=200.0 * n / 1024)
+        out = br.OUT_SPECTRA | br.OUT_BINS | br.OUT_ROWS | br.OUT_WAVES
+        got, ref = run_both(br, oracle, s, cfg, out)
+        assert br.last_kernel() in ("sliding_overlap", "sliding_staged")
+        check_planes(br, got, ref, cfg)
+
+
 @pytest.mark.parametrize("n", [512, 1024])
 def test_overlap_kernel_rows_bit_identical_to_phase_kernel_and_repeatable(br, n):
     """Spectra + rows run the producer / consumer kernel (selection beside the chains, named

@@ -35,7 +35,7 @@ def emu():
 # (N, T, S) as launched by ws_sliding.cu::pick_plan, plus off-nominal tilings
 PLANS = [(256, 128, 16), (512, 64, 8), (1024, 32, 4), (2048, 16, 2), (4096, 8, 1),
          (1024, 16, 1), (1024, 64, 8), (512, 24, 3), (1024, 8, 2),
-         (1024, 32, 2), (1024, 32, 1), (512, 64, 4), (2048, 16, 1), (256, 128, 4)]   # shapes of the producer/consumer kernel
+         (1024, 32, 2), (1024, 32, 1), (512, 64, 4), (2048, 16, 1), (256, 128, 4), (1024, 40, 2)]   # shapes of the producer/consumer kernel
 
 
 @pytest.mark.parametrize("n,t,s", PLANS)
