@@ -793,7 +793,7 @@ def test_overlap_kernel_ragged_tiles_against_oracle(br, oracle, n, tile):
     length: one window, one short of a tile, exactly one, one more, and two tiles plus a ragged third."""
     for nwin in (1, tile - 1, tile, tile + 1, 2 * tile + 7):
         s = synth.random_walk(1300 + n + nwin, n + nwin - 1)
-        cfg = br.default_cfg(n, top_k=8, min_period=18.0 * n / 1024, max_period=200.0 * n / 1024)
+        cfg = br.default_cfg(n, top_k=8, min_period=18.0, max_period=200.0)
         out = br.OUT_SPECTRA | br.OUT_BINS | br.OUT_ROWS | br.OUT_WAVES
         got, ref = run_both(br, oracle, s, cfg, out)
         assert br.last_kernel() in ("sliding_overlap", "sliding_staged")
