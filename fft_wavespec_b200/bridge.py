@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwavespec.so")
+LIB_PATH = os.environ.get("WAVESPEC_LIB") or os.path.join(_HERE, "libwavespec.so")   # WAVESPEC_LIB: profiling builds
 
 # status codes: WaveCyclesBatchFetcher.mq5:15-21
 OK, BAD_ARGS, BACKEND_UNAVAILABLE, TIMEOUT, INTERNAL_ERROR, NOT_READY, NO_MEM = 0, -1, -2, -3, -4, -5, -6

@@ -191,21 +191,42 @@ __global__ void wkalman_kernel(const double* __restrict__ contrib, const int32_t
 
 // ---- A13: persistent period tracker pool + 12 stable slots -------------------------------------
 // Legacy/WaveSpecZZ_1.0.3-pla-kalman-fast.mq5:1415-1667, driven per bar as in :3450-3504.
-// One series per thread, strictly sequential over bars AND over the band candidates of a bar
-// (each UpdateTracker rewrites the period later candidates are matched against).  State lives
-// in global memory (one TrackerState per series) so that window chunks can be chained.
+// One series per WARP, strictly sequential over bars AND over the band candidates of a bar (each
+// UpdateTracker rewrites the period later candidates are matched against).  What is parallel is the
+// inside of a step: the lanes scan the tracker pool for the closest active tracker (the reference's
+// first-strictly-smallest rule = argmin over (difference, index)), and the refill of free slots
+// (first strictly largest power = argmax over (power desc, index asc)).  The pool lives in shared
+// memory while the kernel runs and in global memory (one TrackerState per series) between window
+// chunks.  Round 1 walked it with one thread per series out of global memory: ~10 ms for the 38 bars
+// the structure needs to settle, whatever the series count.
 // The reference quirks are kept: inactive trackers are never re-matched (:1437), erasing shifts
 // the array while the slot table keeps raw indices (:1514-1519, :1584-1589).
-__global__ void tracker_kernel(const double2* __restrict__ band, int32_t band_lo, int32_t nband,
-                               int32_t n_series, int64_t chunk_nwin, int64_t n_process, int64_t win_offset,
-                               int64_t nwin, int32_t N, double tol, int32_t max_inactive,
-                               TrackerState* __restrict__ states, int32_t* __restrict__ trk_index,
-                               double* __restrict__ trk_period) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32)
+tracker_kernel(const double2* __restrict__ band, int32_t band_lo, int32_t nband,
+               int32_t n_series, int64_t chunk_nwin, int64_t n_process, int64_t win_offset,
+               int64_t nwin, int32_t N, double tol, int32_t max_inactive,
+               TrackerState* __restrict__ states, int32_t* __restrict__ trk_index,
+               double* __restrict__ trk_period) {
+    constexpr unsigned kFull = 0xffffffffu;
+    __shared__ double sh_period[kTrackerCap], sh_power[kTrackerCap];
+    __shared__ int32_t sh_index[kTrackerCap], sh_active[kTrackerCap], sh_inactive[kTrackerCap];
+    __shared__ int32_t sh_slot[12];
+    const int s = blockIdx.x;
+    const int lane = threadIdx.x;
     if (s >= n_series) return;
     TrackerState& st = states[s];
-    if (win_offset == 0) { st.count = 0; for (int i = 0; i < 12; i++) st.slot[i] = -1; }
-    int count = st.count;
+    int count = 0;
+    if (win_offset == 0) {
+        if (lane < 12) sh_slot[lane] = -1;
+    } else {
+        count = st.count;
+        for (int i = lane; i < count; i += 32) {
+            sh_period[i] = st.period[i]; sh_power[i] = st.power[i]; sh_index[i] = st.fft_index[i];
+            sh_active[i] = st.is_active[i]; sh_inactive[i] = st.bars_inactive[i];
+        }
+        if (lane < 12) sh_slot[lane] = st.slot[lane];
+    }
+    __syncwarp();
     for (int64_t wl = 0; wl < n_process; wl++) {
         const double2* bw = band + ((int64_t)s * chunk_nwin + wl) * nband;
         for (int c = 0; c < nband; c++) {
@@ -214,11 +235,12 @@ __global__ void tracker_kernel(const double2* __restrict__ band, int32_t band_lo
             if (period <= 0) continue;
             const double2 x = bw[c];
             const double power = (x.x * x.x) + (x.y * x.y);
+            // FindClosestTracker (:1433-1452): lane-strided scan in ascending index, then the warp's argmin
             int best = -1;
             double smallest = 999999;
-            for (int i = 0; i < count; i++) {
-                if (st.bars_inactive[i] > 0) continue;
-                const double tp = st.period[i];
+            for (int i = lane; i < count; i += 32) {
+                if (sh_inactive[i] > 0) continue;
+                const double tp = sh_period[i];
                 const double diff = fabs(tp - period);
                 bool same = false;
                 if (period > 0 && tp > 0) {
@@ -229,69 +251,95 @@ __global__ void tracker_kernel(const double2* __restrict__ band, int32_t band_lo
                 }
                 if (same && diff < smallest) { smallest = diff; best = i; }
             }
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                const double os = __shfl_xor_sync(kFull, smallest, m);
+                const int ob = __shfl_xor_sync(kFull, best, m);
+                if (ob >= 0 && (best < 0 || os < smallest || (os == smallest && ob < best))) { smallest = os; best = ob; }
+            }
             if (best >= 0) {
-                st.period[best] = period; st.fft_index[best] = j; st.power[best] = power;
-                st.is_active[best] = 1; st.bars_inactive[best] = 0;
+                if (lane == 0) {
+                    sh_period[best] = period; sh_index[best] = j; sh_power[best] = power;
+                    sh_active[best] = 1; sh_inactive[best] = 0;
+                }
             } else if (count < kTrackerCap) {
-                st.period[count] = period; st.fft_index[count] = j; st.power[count] = power;
-                st.is_active[count] = 1; st.bars_inactive[count] = 0;
+                if (lane == 0) {
+                    sh_period[count] = period; sh_index[count] = j; sh_power[count] = power;
+                    sh_active[count] = 1; sh_inactive[count] = 0;
+                }
                 count++;
             }
+            __syncwarp();
         }
-        for (int i = count - 1; i >= 0; i--) {
-            if (!st.is_active[i]) {
-                st.bars_inactive[i]++;
-                if (st.bars_inactive[i] >= max_inactive) {
-                    for (int j = i; j < count - 1; j++) {
-                        st.period[j] = st.period[j + 1]; st.power[j] = st.power[j + 1];
-                        st.fft_index[j] = st.fft_index[j + 1]; st.is_active[j] = st.is_active[j + 1];
-                        st.bars_inactive[j] = st.bars_inactive[j + 1];
+        // DeactivateUnseenTrackers (:1497-1529): the descending erase-shift loop visits every tracker
+        // once, so it is a stable compaction of the survivors
+        if (lane == 0) {
+            int w = 0;
+            for (int i = 0; i < count; i++) {
+                bool keep = true;
+                if (!sh_active[i]) { sh_inactive[i]++; keep = sh_inactive[i] < max_inactive; }
+                if (keep) {
+                    if (w != i) {
+                        sh_period[w] = sh_period[i]; sh_power[w] = sh_power[i]; sh_index[w] = sh_index[i];
+                        sh_active[w] = sh_active[i]; sh_inactive[w] = sh_inactive[i];
                     }
-                    count--;
+                    w++;
                 }
             }
+            count = w;
         }
-        for (int i = 0; i < count; i++) st.is_active[i] = 0;
-        // UpdateStableSlots
-        for (int q = 0; q < 12; q++) { int t = st.slot[q]; if (t < 0 || t >= count) st.slot[q] = -1; }
+        count = __shfl_sync(kFull, count, 0);
+        __syncwarp();
+        for (int i = lane; i < count; i += 32) sh_active[i] = 0;
+        // UpdateStableSlots (:1570-1667)
+        if (lane < 12) { const int t = sh_slot[lane]; if (t < 0 || t >= count) sh_slot[lane] = -1; }
+        __syncwarp();
         const int64_t o = ((int64_t)s * nwin + win_offset + wl) * 12;
-        int free_slots = 0;
         for (int q = 0; q < 12; q++) {
-            int t = st.slot[q];
-            if (t >= 0) { trk_period[o + q] = st.period[t]; trk_index[o + q] = st.fft_index[t]; }
-            else free_slots++;
-        }
-        if (free_slots) {
-            // free slots take the strongest unused trackers in the order of the reference's stable
-            // descending bubble sort: larger power first, equal powers keep ascending index
-            for (int q = 0; q < 12; q++) {
-                if (st.slot[q] >= 0) continue;
+            int t = sh_slot[q];                       // uniform
+            if (t < 0) {
+                // the strongest unused tracker in the order of the reference's stable descending
+                // bubble sort: larger power first, equal powers keep ascending index
                 int chosen = -1; double bp = 0.0;
-                for (int i = 0; i < count; i++) {
+                for (int i = lane; i < count; i += 32) {
                     bool used = false;
-                    for (int r = 0; r < 12; r++) used |= (st.slot[r] == i);
+#pragma unroll
+                    for (int r = 0; r < 12; r++) used |= (sh_slot[r] == i);
                     if (used) continue;
-                    const double pw = st.power[i];
+                    const double pw = sh_power[i];
                     if (chosen < 0 || pw > bp) { chosen = i; bp = pw; }
                 }
-                if (chosen >= 0) {
-                    st.slot[q] = chosen;
-                    trk_period[o + q] = st.period[chosen]; trk_index[o + q] = st.fft_index[chosen];
-                } else {
-                    trk_period[o + q] = 0.0; trk_index[o + q] = 0;
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) {
+                    const double op = __shfl_xor_sync(kFull, bp, m);
+                    const int oc = __shfl_xor_sync(kFull, chosen, m);
+                    if (oc >= 0 && (chosen < 0 || op > bp || (op == bp && oc < chosen))) { bp = op; chosen = oc; }
                 }
+                t = chosen;
+                __syncwarp();
+                if (lane == 0) sh_slot[q] = chosen;
+                __syncwarp();
+            }
+            if (lane == 0) {
+                if (t >= 0) { trk_period[o + q] = sh_period[t]; trk_index[o + q] = sh_index[t]; }
+                else { trk_period[o + q] = 0.0; trk_index[o + q] = 0; }
             }
         }
+        __syncwarp();
     }
-    st.count = count;
+    for (int i = lane; i < count; i += 32) {
+        st.period[i] = sh_period[i]; st.power[i] = sh_power[i]; st.fft_index[i] = sh_index[i];
+        st.is_active[i] = sh_active[i]; st.bars_inactive[i] = sh_inactive[i];
+    }
+    if (lane < 12) st.slot[lane] = sh_slot[lane];
+    if (lane == 0) st.count = count;
 }
 
 cudaError_t launch_tracker(const double2* band, int32_t band_lo, int32_t nband, int32_t n_series,
                            int64_t chunk_nwin, int64_t n_process, int64_t win_offset, int64_t nwin, int32_t N,
                            double tol, int32_t max_inactive, TrackerState* states, int32_t* trk_index,
                            double* trk_period, cudaStream_t stream) {
-    const int threads = 32;
-    tracker_kernel<<<(n_series + threads - 1) / threads, threads, 0, stream>>>(
+    tracker_kernel<<<n_series, 32, 0, stream>>>(
         band, band_lo, nband, n_series, chunk_nwin, n_process, win_offset, nwin, N, tol, max_inactive, states,
         trk_index, trk_period);
     return cudaGetLastError();
