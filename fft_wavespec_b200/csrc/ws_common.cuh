@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 
 namespace ws {
 
@@ -68,14 +69,13 @@ __device__ __forceinline__ bool better(double p, int pos, double bp, int bpos) {
 
 // Host side: true the first time a kernel instantiation is launched on the current device (the
 // opt-in dynamic shared-memory size is a per-device function attribute).  `seen` is the caller's
-// static bit mask; a lost update only repeats a harmless cudaFuncSetAttribute.
-inline bool first_launch_on_device(unsigned long long& seen) {
+// static bit mask, one bit per device; launches come from several host threads (one worker per
+// device), hence the atomic.
+inline bool first_launch_on_device(std::atomic<unsigned long long>& seen) {
     int dev = 0;
     cudaGetDevice(&dev);
     const unsigned long long bit = 1ull << (dev & 63);
-    if (seen & bit) return false;
-    seen |= bit;
-    return true;
+    return (seen.fetch_or(bit) & bit) == 0;
 }
 
 }  // namespace ws

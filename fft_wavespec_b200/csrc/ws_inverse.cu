@@ -71,7 +71,7 @@ static cudaError_t launch_inv(const double* d_spec, const int32_t* d_bins, int32
                               const double2* tw, double* d_out, cudaStream_t stream) {
     constexpr int M = (1 << LN) / 2;
     const size_t smem = (size_t)W * M * 16 + (size_t)W * ((M + 31) / 32) * 4;
-    static unsigned long long attr_seen = 0;
+    static std::atomic<unsigned long long> attr_seen{0};
     if (first_launch_on_device(attr_seen)) {
         cudaError_t e = cudaFuncSetAttribute(inverse_real_warp_kernel<LN, W>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);

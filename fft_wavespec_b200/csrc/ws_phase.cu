@@ -124,7 +124,7 @@ cudaError_t launch_phase_from_spectra(const double* spectra, int64_t spec_nwin, 
     int warps = kMaxPhaseWarps;
     while (warps > 1 && warps * per_warp > 113 * 1024) warps >>= 1;      // two CTAs per SM where possible
     const size_t smem = warps * per_warp;
-    static unsigned long long attr_seen = 0;
+    static std::atomic<unsigned long long> attr_seen{0};
     if (first_launch_on_device(attr_seen)) {
         cudaError_t e = cudaFuncSetAttribute(phase_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;

@@ -98,8 +98,12 @@ struct TopSink {
         if (SPEC) { gpP = g + m * N2 + k; gpM = g + m * N2 - k; }
         if (SEL) { xpP = xb + (m * band - lo) + k; xpM = xb + (m * band - lo) - k; }
     }
-    // (a branch-free form with predicated stores was measured: the chain then spills and the top pass
-    // of a 40-window tile takes 38.0k instead of 35.3k cycles — kept as branches)
+    // The validity test costs a branch per store group (10 % of the chain's instructions).  Two ways of
+    // removing it were measured — predicated stores, and a second chain instance without the test for
+    // full tiles (398 instead of 485 instructions per four windows) — and both made the top pass of a
+    // 40-window tile SLOWER (38.0k and 35.5k against 31.9k cycles): without the reconvergence points
+    // ptxas schedules more values live across the stores and the chain spills under the 128-register
+    // cap.  The chain is bound by its stores' register hand-over to the LSU, not by instruction count.
     template <int J> __device__ __forceinline__ void put(double2 v) {
         if (!ok) return;
         constexpr int c = SlotOf<J, TOP>::c * Q;
@@ -620,7 +624,7 @@ bool sliding_shared_supported(const Params& p) {
 
 template <int N, bool SPEC, int CAP, int TOP>
 static cudaError_t launch_top(const Params& p, const Plan& pl, const SlideLayout& lay, cudaStream_t stream) {
-    static unsigned long long attr_seen = 0;
+    static std::atomic<unsigned long long> attr_seen{0};
     if (first_launch_on_device(attr_seen)) {
         cudaError_t e = cudaFuncSetAttribute(sliding_shared_kernel<N, SPEC, CAP, TOP>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
@@ -634,7 +638,7 @@ static cudaError_t launch_top(const Params& p, const Plan& pl, const SlideLayout
 template <int N, bool SPEC>
 static cudaError_t launch_overlap(const Params& p, const Plan& pl, const SlideLayout& lay, cudaStream_t stream) {
     if (N > 2048) return cudaErrorInvalidValue;          // chains of N = 4096 need all eight warps
-    static unsigned long long attr_seen = 0;
+    static std::atomic<unsigned long long> attr_seen{0};
     if (first_launch_on_device(attr_seen)) {
         cudaError_t e = cudaFuncSetAttribute(sliding_overlap_kernel<N, SPEC>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
@@ -651,14 +655,14 @@ static cudaError_t launch_staged(const Params& p, const Plan& pl, const SlideLay
     else {
     dim3 grid((unsigned)((p.chunk_nwin + pl.T - 1) / pl.T), (unsigned)p.n_series);
     if (lay.ring_slots == 4) {
-        static unsigned long long attr_seen = 0;
+        static std::atomic<unsigned long long> attr_seen{0};
         if (first_launch_on_device(attr_seen)) {
             cudaError_t e = cudaFuncSetAttribute(sliding_staged_kernel<N, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
             if (e != cudaSuccess) return e;
         }
         sliding_staged_kernel<N, 4><<<grid, kSlideThreads, lay.total_bytes, stream>>>(p, pl, lay);
     } else {
-        static unsigned long long attr_seen = 0;
+        static std::atomic<unsigned long long> attr_seen{0};
         if (first_launch_on_device(attr_seen)) {
             cudaError_t e = cudaFuncSetAttribute(sliding_staged_kernel<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
             if (e != cudaSuccess) return e;

@@ -344,7 +344,7 @@ template <int NT, int LN, int CAP>
 static cudaError_t launch_nt(Params p, cudaStream_t stream) {
     p.tile_windows = window_fft_pick_tile(p, NT);
     size_t smem = window_fft_smem_bytes(p, p.tile_windows, NT);
-    static unsigned long long attr_seen = 0;
+    static std::atomic<unsigned long long> attr_seen{0};
     if (first_launch_on_device(attr_seen)) {
         cudaError_t e = cudaFuncSetAttribute(window_fft_kernel<NT, LN, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;

@@ -172,7 +172,7 @@ template <int LN, int kWarps, int MINB>
 static cudaError_t launch_ln(Params p, cudaStream_t stream) {
     p.tile_windows = warp_pick_tile(p, kWarps);
     const WarpLayout L = warp_layout(p, p.tile_windows, kWarps);
-    static unsigned long long attr_seen = 0;
+    static std::atomic<unsigned long long> attr_seen{0};
     if (first_launch_on_device(attr_seen)) {
         cudaError_t e = cudaFuncSetAttribute(window_fft_warp_kernel<LN, kWarps, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
