@@ -195,3 +195,59 @@ def test_jobs_spread_over_every_device(oracle):
     finally:
         br.gpu_shutdown()
         assert br.gpu_init(0, 8) == br.OK
+
+
+def test_free_and_shutdown_with_jobs_in_flight(br, oracle):
+    """OnDeinit frees whatever is still queued and shuts the session down (WaveSpecZZ_1.1.0-gpuopt.mq5:
+    698-720): neither may wait for, or trip over, work that is still running; a new session works."""
+    s = synth.random_walk(61, 400_000)
+    jobs = []
+    for _ in range(6):
+        st, jid = br.gpu_submit_extract_cycles_batch(s, 1024, 1, 8, 18.0, 200.0, 60.0, 0, 10, 15)
+        assert st == br.OK
+        jobs.append(jid)
+    out = pinned((400_000 - 1023) * 8 * 15)
+    br.gpu_try_get_cycles_batch(jobs[0], out)              # arm one of them: copies in flight into `out`
+    for jid in jobs[:3]:
+        assert br.gpu_free_job(jid) == br.OK               # freed while running (job 0 with an armed buffer)
+    br.gpu_shutdown()                                      # three jobs still in the table
+    st, n, ready = br.gpu_try_get_cycles_batch(jobs[4], out)
+    assert st == br.BAD_ARGS                               # ids of the old session are gone (and the
+    assert br.gpu_init(0, 8) == br.OK                      # library says so instead of crashing)
+    x = synth.random_walk(62, 3000)
+    st, jid = br.gpu_submit_extract_cycles_batch(x, 1024, 1, 4, 9.0, 200.0, 60.0, 0, 10, 15)
+    assert st == br.OK
+    res = np.empty((3000 - 1023) * 4 * 15)
+    assert poll(br, br.gpu_try_get_cycles_batch, jid, res) == (3000 - 1023) * 4
+    assert br.gpu_free_job(jid) == br.OK
+    cfg = oracle.default_cfg(1024, top_k=4, min_period=9.0, max_period=200.0)
+    ref = oracle.pipeline_series(x, cfg, oracle.OUT_BINS)
+    assert np.array_equal(np.rint(1024 / res.reshape(-1, 4, 15)[..., 2]).astype(int), ref["bins"])
+
+
+def test_two_host_threads_share_the_session(br, oracle):
+    """Several indicator instances and the Fetcher can live in one process (threading):
+    two host threads submit, poll and free their own jobs at the same time."""
+    import threading
+    errors = []
+
+    def client(seed):
+        try:
+            cfg = oracle.default_cfg(512, top_k=4, min_period=9.0, max_period=100.0)
+            for r in range(6):
+                s = synth.random_walk(seed + r, 512 + 2500)
+                st, jid = br.gpu_submit_extract_cycles_batch(s, 512, 1, 4, 9.0, 100.0, 60.0, 0, 10, 15)
+                assert st == br.OK, br.last_error()
+                out = np.empty(2501 * 4 * 15)
+                assert poll(br, br.gpu_try_get_cycles_batch, jid, out) == 2501 * 4
+                assert br.gpu_free_job(jid) == br.OK
+                ref = oracle.pipeline_series(s, cfg, oracle.OUT_BINS)
+                assert np.array_equal(np.rint(512 / out.reshape(-1, 4, 15)[..., 2]).astype(int), ref["bins"])
+                w = br.gpu_fft_real_forward(s[:512])           # synchronous calls interleave with the jobs
+                assert np.abs(w - oracle.fft_interleaved(s[:512])).max() <= 1e-9 * np.abs(w).max()
+        except Exception as e:                                 # noqa: BLE001
+            errors.append(repr(e))
+    th = [threading.Thread(target=client, args=(8000 + 100 * i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
