@@ -79,22 +79,29 @@ __device__ __forceinline__ void warp_select_emit_x(const Params& p, double* pw, 
             __syncwarp();
             if (lane == r) { my_bin = sel; my_pow = bp; }
         }
-    } else if (hi - lo < 64) {
-        // narrow band (the usual case): each lane keeps its two candidates in registers, so a
-        // round is a compare, the warp argmax and a conditional retire — no shared-memory traffic.
-        // NaN powers never win (as in the scan below): they are retired up front.
-        const int b0 = lo + lane, b1 = lo + 32 + lane;
-        double v0 = -2.0, v1 = -2.0;
-        if (b0 <= hi) { v0 = pw[b0]; if (!(v0 >= 0.0)) v0 = -2.0; }
-        if (b1 <= hi) { v1 = pw[b1]; if (!(v1 >= 0.0)) v1 = -2.0; }
+    } else if (hi - lo < 128) {
+        // bands up to 128 bins (the usual cases: 51 bins at N = 1024 / 18-200, 74 at N = 2048 / 18-52):
+        // each lane keeps its up to four candidates in registers, so a round is three compares, the warp
+        // argmax and a conditional retire — no shared-memory traffic.  Within a lane the candidates are
+        // in ascending bin order and the compares are strict, so an equal power never displaces the
+        // lower bin.  NaN powers never win (as in the scan below): they are retired up front.
+        int bb[4];
+        double v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            bb[i] = lo + 32 * i + lane;
+            v[i] = -2.0;
+            if (bb[i] <= hi) { v[i] = pw[bb[i]]; if (!(v[i] >= 0.0)) v[i] = -2.0; }
+        }
         for (int r = 0; r < K; r++) {
-            double bp = v0; int bpos = b0;
-            if (v1 > bp) { bp = v1; bpos = b1; }
+            double bp = v[0]; int bpos = bb[0];
+#pragma unroll
+            for (int i = 1; i < 4; i++) if (v[i] > bp) { bp = v[i]; bpos = bb[i]; }
             if (bp < 0.0) { bp = -1.0; bpos = 0x7fffffff; }
             warp_argbest(bp, bpos);
             if (bpos == 0x7fffffff) break;              // band exhausted: remaining slots stay -1
-            if (bpos == b0) v0 = -2.0;
-            if (bpos == b1) v1 = -2.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) if (bpos == bb[i]) v[i] = -2.0;
             if (lane == r) { my_bin = bpos; my_pow = bp; }
         }
     } else {
