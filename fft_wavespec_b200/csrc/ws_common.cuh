@@ -67,6 +67,25 @@ __device__ __forceinline__ bool better(double p, int pos, double bp, int bpos) {
     return (p > bp) || (p == bp && pos < bpos);
 }
 
+// Stages samples [0, count) of `g` into shared x[0, count) with 128-bit global loads: the run is split
+// at its first 16-byte boundary (a window tile starts at an arbitrary sample, so `g` is 0 or 8 mod
+// 16), the aligned middle moves as double2, and the odd sample at either end moves alone.  Only the
+// first `valid` samples exist (a tile may run past the end of its series): the rest read as 0.
+__device__ __forceinline__ void stage_samples(const double* __restrict__ g, int count, int valid, double* x,
+                                              int tid, int nthreads) {
+    const int n = valid < 0 ? 0 : (valid < count ? valid : count);
+    const int head = (int)((reinterpret_cast<unsigned long long>(g) >> 3) & 1ull);
+    if (tid == 0 && head) x[0] = n > 0 ? g[0] : 0.0;
+    const int pairs = n > head ? (n - head) >> 1 : 0;
+    const double2* g2 = reinterpret_cast<const double2*>(g + head);
+    for (int j = tid; j < pairs; j += nthreads) {
+        const double2 v = g2[j];
+        x[head + 2 * j] = v.x;
+        x[head + 2 * j + 1] = v.y;
+    }
+    for (int i = head + 2 * pairs + tid; i < count; i += nthreads) x[i] = (i < n) ? g[i] : 0.0;
+}
+
 // Host side: true the first time a kernel instantiation is launched on the current device (the
 // opt-in dynamic shared-memory size is a per-device function attribute).  `seen` is the caller's
 // static bit mask, one bit per device; launches come from several host threads (one worker per

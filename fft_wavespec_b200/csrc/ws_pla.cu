@@ -12,9 +12,12 @@
 // trees are nearly the same — but only nearly, and a warp whose lanes drift apart inside a
 // data-dependent `while` executes them one after the other (measured on the first version of this
 // kernel: 176 cycles per loop iteration, 9.8 M windows/s).  The walk is therefore written in warp
-// LOCKSTEP: every trip of the outer loop pops one node per lane, the fit / error / render loops run
-// to the longest segment of the warp with shorter lanes predicated off, and nothing in the body
-// branches on lane data across a loop.  Each lane's arithmetic and its order are untouched.
+// LOCKSTEP: every trip of the outer loop handles at most one node per lane, the fit / error / render
+// loops run to the longest participating segment with shorter lanes predicated off, and nothing in
+// the body branches on lane data across a loop.  A trip is given to the lanes whose next segment is
+// the same one in absolute bar coordinates (see the loop head): lanes whose trees have drifted wait
+// for their turn instead of stretching every trip to the longest of 32 unrelated segments.  Each
+// lane's arithmetic and its order are untouched.
 // Leaves are rendered by the lane that owns them, in append order (later segments overwrite earlier
 // ones as in :487-495); no shared memory, so occupancy is bounded by registers only.
 //
@@ -51,9 +54,25 @@ pla_kernel(const double* __restrict__ series, int64_t series_stride, int64_t nwi
     const double maxerr = max_error < 1e-8 ? 1e-8 : max_error;
 
     while (__any_sync(kFull, sp > 0)) {
-        const bool on = sp > 0;
+        // Which lanes take this trip.  In absolute bar coordinates the trees of neighbouring windows are
+        // the same wherever they agree (a split at bar b is a split at bar b for every window that
+        // contains it); segments that touch a window edge get a common key.  Pre-order is ascending in
+        // (start asc, end desc), so the trip goes to the lanes whose next segment is the earliest one —
+        // and every lane whose next segment is the same one up to two samples at either end.  Lanes
+        // further along wait: a trip then costs one segment class instead of the longest of 32
+        // unrelated segments.  Only the SCHEDULE depends on this; each lane still walks its own stack
+        // in its own order.
+        const bool has = sp > 0;
         int s = 0, e = -1;
-        if (on) { --sp; s = stk_s[sp]; e = stk_e[sp]; }
+        if (has) { s = stk_s[sp - 1]; e = stk_e[sp - 1]; }
+        const long long bar0 = w * hop;                       // absolute bar of the window's first sample
+        const unsigned a_s = !has ? 0xffffffffu : (s == 0 ? 0u : (unsigned)(bar0 + s) + 1u);
+        const unsigned a_e = !has ? 0u : (e == N - 1 ? 0xffffffffu : (unsigned)(bar0 + e));
+        const unsigned as0 = __reduce_min_sync(kFull, a_s);
+        const unsigned ae0 = __reduce_max_sync(kFull, (has && a_s == as0) ? a_e : 0u);
+        const long long das = (long long)a_s - (long long)as0, dae = (long long)a_e - (long long)ae0;
+        const bool on = has && das <= 2 && dae <= 2 && dae >= -2;
+        if (on) --sp;
         const bool fit = on && s < e;
         const int len = fit ? e - s + 1 : 0;
         const int len_max = __reduce_max_sync(kFull, len);

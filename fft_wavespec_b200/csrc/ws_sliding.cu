@@ -6,8 +6,8 @@
 // band-limited top-K selection and row pack (:537-568 of the latter).
 //
 // One CTA owns a tile of T consecutive windows of one series:
-//   1. the T + N - 1 samples of the tile are staged in shared memory (each sample is read from
-//      HBM once per tile);
+//   1. the T + N - 1 samples of the tile are staged in shared memory with 128-bit loads (each
+//      sample is read from HBM once per tile);
 //   2. the deepest decimation level is computed directly from the samples (2..16-point DFTs);
 //   3. fused radix-8 passes (ws_sliding_core.cuh) build the level-3 vectors in shared memory,
 //      sharing every sub-transform between the overlapping windows of the tile;
@@ -135,9 +135,9 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     const int nvalid = (int)((wend - w0) < pl.T ? (wend - w0) : pl.T);
 
     // 1. stage the tile (+ halo); beyond the series the samples only feed windows that are never stored
-    for (int i = tid; i < pl.x_len; i += NT) {
-        int64_t a = w0 + i;
-        x[i] = (a < p.series_len) ? src[a] : 0.0;
+    {
+        const int64_t left = (int64_t)p.series_len - w0;
+        stage_samples(src + w0, pl.x_len, left > pl.x_len ? pl.x_len : (int)left, x, tid, NT);
     }
     __syncthreads();
     // 2. deepest level straight from the samples
@@ -241,9 +241,9 @@ sliding_overlap_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     const double* src = p.series + (int64_t)s * p.series_stride;
     const int nvalid = (int)((wend - w0) < pl.T ? (wend - w0) : pl.T);
 
-    for (int i = tid; i < pl.x_len; i += kSlideThreads) {
-        int64_t a = w0 + i;
-        x[i] = (a < p.series_len) ? src[a] : 0.0;
+    {
+        const int64_t left = (int64_t)p.series_len - w0;
+        stage_samples(src + w0, pl.x_len, left > pl.x_len ? pl.x_len : (int)left, x, tid, kSlideThreads);
     }
     __syncthreads();
     ws_slide::bottom_level(tid, kSlideThreads, x, pl, p.tw, arena);
@@ -392,9 +392,9 @@ sliding_staged_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     const double* src = p.series + (int64_t)s * p.series_stride;
     const int nvalid = (int)((wend - w0) < pl.T ? (wend - w0) : pl.T);
 
-    for (int i = tid; i < pl.x_len; i += kSlideThreads) {
-        int64_t a = w0 + i;
-        x[i] = (a < p.series_len) ? src[a] : 0.0;
+    {
+        const int64_t left = (int64_t)p.series_len - w0;
+        stage_samples(src + w0, pl.x_len, left > pl.x_len ? pl.x_len : (int)left, x, tid, kSlideThreads);
     }
     __syncthreads();
     ws_slide::bottom_level(tid, kSlideThreads, x, pl, p.tw, arena);

@@ -75,7 +75,7 @@ window_fft_warp_kernel(const Params p, const WarpLayout L) {
 
     // ---- tile prologue (whole CTA): stage the samples, run the trend IIR once per tile
     const double* src = p.series + (int64_t)s * p.series_stride + w0 * p.hop;
-    for (int i = tid; i < Lt; i += kThreads) tile[i] = src[i];
+    stage_samples(src, Lt, Lt, tile, tid, kThreads);            // 128-bit loads, split at the 16-byte boundary
     __syncthreads();
     if (p.detrend == 1) {
         // Trend IIR (Legacy/...-kalman-fast.mq5:3367-3379) restarted per window:
