@@ -12,12 +12,12 @@
 // trees are nearly the same — but only nearly, and a warp whose lanes drift apart inside a
 // data-dependent `while` executes them one after the other (measured on the first version of this
 // kernel: 176 cycles per loop iteration, 9.8 M windows/s).  The walk is therefore written in warp
-// LOCKSTEP: every trip of the outer loop handles at most one node per lane, the fit / error / render
-// loops run to the longest participating segment with shorter lanes predicated off, and nothing in
-// the body branches on lane data across a loop.  A trip is given to the lanes whose next segment is
-// the same one in absolute bar coordinates (see the loop head): lanes whose trees have drifted wait
-// for their turn instead of stretching every trip to the longest of 32 unrelated segments.  Each
-// lane's arithmetic and its order are untouched.
+// LOCKSTEP: every trip of the outer loop pops one node per lane and the warp reconverges after each of
+// the fit / error / render loops of the trip (lanes with shorter segments drop out of a loop early, so
+// a trip costs its longest segment).  Each lane's arithmetic and its order are untouched.
+// (Measured and rejected: giving a trip only to the lanes whose next segment is the same one in
+// absolute bar coordinates, plus the lanes with shorter segments — 1.74x instead of 2.07x a lane's own
+// work in simulation, but the extra trips cost it back on the device: 16.3 vs 17.1 M windows/s.)
 // Leaves are rendered by the lane that owns them, in append order (later segments overwrite earlier
 // ones as in :487-495); no shared memory, so occupancy is bounded by registers only.
 //
@@ -54,44 +54,29 @@ pla_kernel(const double* __restrict__ series, int64_t series_stride, int64_t nwi
     const double maxerr = max_error < 1e-8 ? 1e-8 : max_error;
 
     while (__any_sync(kFull, sp > 0)) {
-        // Which lanes take this trip.  In absolute bar coordinates the trees of neighbouring windows are
-        // the same wherever they agree (a split at bar b is a split at bar b for every window that
-        // contains it); segments that touch a window edge get a common key.  Pre-order is ascending in
-        // (start asc, end desc), so the trip goes to the lanes whose next segment is the earliest one —
-        // and every lane whose next segment is the same one up to two samples at either end.  Lanes
-        // further along wait: a trip then costs one segment class instead of the longest of 32
-        // unrelated segments.  Only the SCHEDULE depends on this; each lane still walks its own stack
-        // in its own order.
-        const bool has = sp > 0;
+        const bool on = sp > 0;
         int s = 0, e = -1;
-        if (has) { s = stk_s[sp - 1]; e = stk_e[sp - 1]; }
-        const long long bar0 = w * hop;                       // absolute bar of the window's first sample
-        const unsigned a_s = !has ? 0xffffffffu : (s == 0 ? 0u : (unsigned)(bar0 + s) + 1u);
-        const unsigned a_e = !has ? 0u : (e == N - 1 ? 0xffffffffu : (unsigned)(bar0 + e));
-        const unsigned as0 = __reduce_min_sync(kFull, a_s);
-        const unsigned ae0 = __reduce_max_sync(kFull, (has && a_s == as0) ? a_e : 0u);
-        const long long das = (long long)a_s - (long long)as0, dae = (long long)a_e - (long long)ae0;
-        const bool on = has && das <= 2 && dae <= 2 && dae >= -2;
-        if (on) --sp;
+        if (on) { --sp; s = stk_s[sp]; e = stk_e[sp]; }
         const bool fit = on && s < e;
         const int len = fit ? e - s + 1 : 0;
-        const int len_max = __reduce_max_sync(kFull, len);
 
         // FitPlaSegment (:387-417).  sy and sxy are accumulated in ascending index order exactly as the
         // reference does.  sx = sum i and sx2 = sum i*i are sums of integers far below 2^53: every
         // partial sum of the reference's loop is exact, so the closed forms below are bit-identical to
         // it.  x runs as a double incremented by 1.0 (exact) instead of a conversion per sample.
+        // The loops have per-lane bounds: lanes with shorter segments drop out and the warp reconverges
+        // at the __syncwarp — the trip costs its longest segment, without per-iteration predicate math.
         double sy = 0.0, sxy = 0.0;
         {
             double x = (double)s;
-            for (int t = 0; t < len_max; ++t) {
-                if (t < len) {
-                    const double v = y[s + t];
-                    sy += v; sxy += x * v;
-                    x += 1.0;
-                }
+            const double* yp = y + s;
+            for (int t = 0; t < len; ++t) {
+                const double v = yp[t];
+                sy += v; sxy += x * v;
+                x += 1.0;
             }
         }
+        __syncwarp();
         const long long ls = s, le = e, ln = len;
         const double sx = (double)((ls + le) * ln / 2);
         auto sq = [](long long n) { return n * (n + 1) * (2 * n + 1) / 6; };          // sum_{i=0}^{n} i^2
@@ -112,15 +97,15 @@ pla_kernel(const double* __restrict__ series, int64_t series_stride, int64_t nwi
         int worst = s;
         {
             double x = (double)s;
-            for (int t = 0; t < len_max; ++t) {
-                if (t < len) {
-                    const double approx = slope * x + icpt;
-                    const double err = fabs(y[s + t] - approx);
-                    if (err > mx) { mx = err; worst = s + t; }
-                    x += 1.0;
-                }
+            const double* yp = y + s;
+            for (int t = 0; t < len; ++t) {
+                const double approx = slope * x + icpt;
+                const double err = fabs(yp[t] - approx);
+                if (err > mx) { mx = err; worst = s + t; }
+                x += 1.0;
             }
         }
+        __syncwarp();
         if (fit) {
             const bool can_split = (count + 2) <= maxseg && (e - s) > 1;
             if (can_split && mx > maxerr) {
@@ -143,10 +128,10 @@ pla_kernel(const double* __restrict__ series, int64_t series_stride, int64_t nwi
             ++count;
         }
         if (line_w) {
-            const int rmax = __reduce_max_sync(kFull, rlen);
             double x = (double)s;
-            for (int t = 0; t < rmax; ++t)
-                if (t < rlen) { line_w[s + t] = slope * x + icpt; x += 1.0; }
+            double* lp = line_w + s;
+            for (int t = 0; t < rlen; ++t) { lp[t] = slope * x + icpt; x += 1.0; }
+            __syncwarp();
         }
     }
     if (active) {
