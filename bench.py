@@ -186,10 +186,11 @@ def parity_check(orc, host_np, cfg_o, d_rows, d_spectra, S, G, nwin, rng_seed=12
     return res
 
 
-def e2e_pass(bridge, host_np, outs, submit, getter, units_per_job):
+def e2e_pass(bridge, host_np, outs, submit, getter, units_per_job, verify=None):
     """One pass over every series through the job API, as the reference's callers drive it
     (submit, poll try_get, free; WaveCyclesBatchFetcher.mq5:113-133) with `len(outs)` jobs in
-    flight.  Every job's result lands in a pinned host buffer and one value of it is read."""
+    flight.  Every job's result lands in a pinned host buffer and one value of it is read.
+    verify(series_index, buffer) — untimed passes only — checks a delivered result against the oracle."""
     from collections import deque
     S = host_np.shape[0]
     pending, free_bufs, i, done, acc = deque(), list(range(len(outs))), 0, 0, 0.0
@@ -200,19 +201,48 @@ def e2e_pass(bridge, host_np, outs, submit, getter, units_per_job):
                 raise RuntimeError(f"submit failed {stt}: {bridge.last_error()}")
             b = free_bufs.pop()
             getter(jid, outs[b])                       # first poll arms the buffer: chunks land as they finish
-            pending.append((jid, b)); i += 1
-        jid, b = pending[0]
+            pending.append((jid, b, i)); i += 1
+        jid, b, si = pending[0]
         stt, n, ready = getter(jid, outs[b])
         if stt != bridge.OK:
             raise RuntimeError(f"try_get failed {stt}: {bridge.last_error()}")
         if ready:
             assert n == units_per_job, (n, units_per_job)
             acc += float(outs[b][0]) + float(outs[b][-1])
+            if verify is not None:
+                verify(si, outs[b])
             bridge.gpu_free_job(jid)
             pending.popleft(); free_bufs.append(b); done += 1
         else:
             time.sleep(0.0002)
     return acc
+
+
+def make_e2e_verifier(orc, host_np, cfg_o, product, nwin, every=9):
+    """Checks delivered job results against the oracle on a few windows / bars of every `every`-th series:
+    selected bins exact (period = N / bin), amplitude within 1e-9; for the cache record, bar b < nwin
+    carries slot 0 and slot K-1 of window b at k = 0 (WaveSpecZZ_1.1.0-gpuopt.mq5:1084-1098)."""
+    state = {"checked": 0, "bins_equal": True, "max_rel_err": 0.0}
+    rng = np.random.default_rng(77)
+
+    def verify(si, buf):
+        if si % every:
+            return
+        for w in [int(x) for x in rng.integers(0, nwin, 4)]:
+            ref = orc.pipeline_series(host_np[si, w:w + N_WINDOW], cfg_o, orc.OUT_ROWS | orc.OUT_BINS)
+            r = ref["rows"][0]
+            if product == "rows":
+                got = buf.reshape(nwin, TOP_K, ROW_STRIDE)[w]
+                state["bins_equal"] &= bool(np.array_equal(np.rint(N_WINDOW / got[:, 2]).astype(np.int64), ref["bins"][0]))
+                err = np.abs(got[:, 0] - r[:, 0]).max() / np.abs(r[:, 0]).max()
+            else:
+                rec = buf.reshape(-1, 20)[w]
+                exp = np.array([r[0, 0] * np.sin(r[0, 3]), r[-1, 0] * np.sin(r[-1, 3]), r[0, 2], r[-1, 2]])
+                state["bins_equal"] &= bool(rec[2] == r[0, 2] and rec[3] == r[-1, 2])
+                err = np.abs(rec[:2] - exp[:2]).max() / np.abs(r[:, 0]).max()
+            state["max_rel_err"] = max(state["max_rel_err"], float(err))
+            state["checked"] += 1
+    return verify, state
 
 
 def d2h_ceiling_probe(torch, barrier, reduce_min, reduce_sum, n_bytes=1 << 29, reps=4):
@@ -481,9 +511,14 @@ def main():
     if not args.no_e2e:
         depth = args.e2e_depth
 
-        def measure(submit, getter, out_doubles, units, d2h_bytes):
+        def measure(submit, getter, out_doubles, units, d2h_bytes, product):
             outs = [torch.empty(out_doubles, dtype=torch.float64, pin_memory=True).numpy() for _ in range(depth)]
-            e2e_pass(bridge, host_np, outs, submit, getter, units)         # warm-up (pools, pinned pages)
+            verify = state = None
+            if rank == 0 and not args.no_parity:
+                from oracle import oracle as orc
+                cfg_o = orc.default_cfg(N_WINDOW, top_k=TOP_K, min_period=MIN_P, max_period=MAX_P, row_stride=ROW_STRIDE)
+                verify, state = make_e2e_verifier(orc, host_np, cfg_o, product, nwin)
+            e2e_pass(bridge, host_np, outs, submit, getter, units, verify)   # warm-up (pools, pinned pages), verified
             barrier()
             tt = time.perf_counter()
             for _ in range(args.e2e_steps):
@@ -491,20 +526,29 @@ def main():
             torch.cuda.synchronize()
             dt = max_over_ranks(time.perf_counter() - tt)
             del outs
-            return {"value": world * spectra_per_step * args.e2e_steps / dt, "unit": UNIT,
-                    "h2d_bytes_per_step": world * S * T * 8, "d2h_bytes_per_step": world * S * d2h_bytes,
-                    "ms_per_step": 1e3 * dt / args.e2e_steps, "jobs_in_flight": depth,
-                    "d2h_gb_per_s_per_gpu": S * d2h_bytes * args.e2e_steps / dt / 1e9}
+            res = {"value": world * spectra_per_step * args.e2e_steps / dt, "unit": UNIT,
+                   "h2d_bytes_per_step": world * S * T * 8, "d2h_bytes_per_step": world * S * d2h_bytes,
+                   "ms_per_step": 1e3 * dt / args.e2e_steps, "jobs_in_flight": depth,
+                   "d2h_gb_per_s_per_gpu": S * d2h_bytes * args.e2e_steps / dt / 1e9}
+            if state is not None:
+                res["parity_check"] = {"results_checked": state["checked"], "bins_equal": state["bins_equal"],
+                                       "max_rel_err": state["max_rel_err"], "tolerance": 1e-9,
+                                       "ok": bool(state["checked"] > 0 and state["bins_equal"] and state["max_rel_err"] <= 1e-9),
+                                       "how": "delivered results of the (untimed) warm-up pass against the oracle"}
+            return res
 
-        e2e = measure(lambda x: bridge.submit_cycle_cache_batch(x, N_WINDOW, 1, TOP_K, MIN_P, MAX_P, 60.0, 0, 10),
-                      bridge.try_get_cycle_cache, T * 20, T, T * 20 * 8)
+        # InpMinCoherence = InpMinScore = 0: with the indicator's defaults every FFT-ridge wave is weighted 0
+        # (INTEGRATION.md section 3); the work is the same either way
+        e2e = measure(lambda x: bridge.submit_cycle_cache_batch(x, N_WINDOW, 1, TOP_K, MIN_P, MAX_P, 60.0, 0, 10,
+                                                                min_coherence=0.0, min_score=0.0),
+                      bridge.try_get_cycle_cache, T * 20, T, T * 20 * 8, "record")
         e2e["product"] = ("cycle-cache record: 20 doubles per bar (WaveSpecZZ_1.1.0-gpuopt.mq5:294-324), extraction and "
                           "the decode of :1067-1099 on the device")
         e2e["api"] = "wavespec_submit_cycle_cache_batch / wavespec_try_get_cycle_cache / gpu_free_job, pinned host buffers"
         out_doubles = nwin * TOP_K * ROW_STRIDE
         e2e_rows = measure(lambda x: bridge.gpu_submit_extract_cycles_batch(x, N_WINDOW, 1, TOP_K, MIN_P, MAX_P, 60.0,
                                                                            0, 10, ROW_STRIDE),
-                           bridge.gpu_try_get_cycles_batch, out_doubles, nwin * TOP_K, out_doubles * 8)
+                           bridge.gpu_try_get_cycles_batch, out_doubles, nwin * TOP_K, out_doubles * 8, "rows")
         e2e_rows["product"] = "stride-15 rows: top_k x 15 doubles per window (960 B/window), PCIe bound"
         e2e_rows["api"] = "gpu_submit_extract_cycles_batch / gpu_try_get_cycles_batch / gpu_free_job (imports.mqh), pinned host buffers"
         # both legs are PCIe bound: print the box's concurrent D2H ceiling measured in this run next to them
