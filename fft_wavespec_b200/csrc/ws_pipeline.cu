@@ -306,7 +306,11 @@ int run_pipeline(Device& dev, const double* d_series, int32_t n_series, int32_t 
         auto dispatch_fft = [&](const Params& p) -> int {
             const bool plain = c->hop == 1 && c->detrend == WAVESPEC_DETREND_NONE &&
                                c->window_type == WAVESPEC_WINDOW_NONE && !p.phase;
-            if (plain && ws::sliding_shared_supported(p)) {
+            // a handful of windows (the per-bar calls of the live loop: one window per call) shares
+            // nothing: the per-window kernel transforms exactly those, the sliding kernel a whole tile
+            static const long tiny = [] { const char* e = getenv("WAVESPEC_TINY"); return e ? atol(e) : 0L; }();
+            const bool few = (int64_t)p.n_series * p.chunk_nwin <= tiny && !p.band_buf;
+            if (plain && !few && ws::sliding_shared_supported(p)) {
                 // Two ways to produce rows on this path: the fused in-kernel epilogue (default) or a
                 // hand-off of the in-band bins to a separate full-occupancy rows kernel
                 // (WAVESPEC_SPLIT=1).  Measured on B200 at N=1024 they are within 3 % of each
