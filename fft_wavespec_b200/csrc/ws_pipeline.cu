@@ -308,7 +308,8 @@ int run_pipeline(Device& dev, const double* d_series, int32_t n_series, int32_t 
                                c->window_type == WAVESPEC_WINDOW_NONE && !p.phase;
             // a handful of windows (the per-bar calls of the live loop: one window per call) shares
             // nothing: the per-window kernel transforms exactly those, the sliding kernel a whole tile
-            static const long tiny = [] { const char* e = getenv("WAVESPEC_TINY"); return e ? atol(e) : 0L; }();
+            // (gpu_fft_real_forward(1024): 57 -> 48 us; WAVESPEC_TINY overrides the threshold)
+            static const long tiny = [] { const char* e = getenv("WAVESPEC_TINY"); return e ? atol(e) : 2L; }();
             const bool few = (int64_t)p.n_series * p.chunk_nwin <= tiny && !p.band_buf;
             if (plain && !few && ws::sliding_shared_supported(p)) {
                 // Two ways to produce rows on this path: the fused in-kernel epilogue (default) or a

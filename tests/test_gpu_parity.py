@@ -314,7 +314,8 @@ def test_sliding_shared_kernel_all_lengths_and_ragged_tiles(br, oracle, n):
         cfg = br.default_cfg(n, top_k=8, min_period=9.0, max_period=200.0)
         out = br.OUT_SPECTRA | br.OUT_BINS | br.OUT_ROWS | br.OUT_WAVES
         got = br.pipeline_host(s, cfg, out)
-        assert br.last_kernel() in ("sliding_shared", "sliding_overlap", "sliding_staged")
+        if extra > 0:                                # 2 series x 1 window: the per-window kernel takes it
+            assert br.last_kernel() in ("sliding_shared", "sliding_overlap", "sliding_staged")
         for i in range(2):
             ref = oracle.pipeline_series(s[i], ocfg_from(oracle, cfg), out)
             check_planes(br, {k: v[i] for k, v in got.items()}, ref, cfg)
@@ -796,7 +797,8 @@ def test_overlap_kernel_ragged_tiles_against_oracle(br, oracle, n, tile):
         cfg = br.default_cfg(n, top_k=8, min_period=18.0, max_period=200.0)
         out = br.OUT_SPECTRA | br.OUT_BINS | br.OUT_ROWS | br.OUT_WAVES
         got, ref = run_both(br, oracle, s, cfg, out)
-        assert br.last_kernel() in ("sliding_overlap", "sliding_staged")
+        if nwin > 2:                                 # one or two windows go to the per-window kernel
+            assert br.last_kernel() in ("sliding_overlap", "sliding_staged")
         check_planes(br, got, ref, cfg)
 
 
