@@ -48,6 +48,7 @@ struct Params {
     long long* dbg;            // optional [1024][4] clock64 phase stamps of the first CTAs (WAVESPEC_TIMING_FILE), or nullptr
     int32_t tile_windows;      // windows per CTA tile
     int32_t k1_wpc_cap;        // per-window FFT: max windows transformed concurrently by a CTA
+    int32_t prefetch_tiles;    // sliding kernels: a CTA pulls the new samples of the tile this many tiles ahead into L2 (0: off)
 };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -75,15 +76,46 @@ __device__ __forceinline__ void stage_samples(const double* __restrict__ g, int 
                                               int tid, int nthreads) {
     const int n = valid < 0 ? 0 : (valid < count ? valid : count);
     const int head = (int)((reinterpret_cast<unsigned long long>(g) >> 3) & 1ull);
-    if (tid == 0 && head) x[0] = n > 0 ? g[0] : 0.0;
     const int pairs = n > head ? (n - head) >> 1 : 0;
     const double2* g2 = reinterpret_cast<const double2*>(g + head);
-    for (int j = tid; j < pairs; j += nthreads) {
-        const double2 v = g2[j];
-        x[head + 2 * j] = v.x;
-        x[head + 2 * j + 1] = v.y;
+    // All of a thread's loads are issued before its first store: the tile is staged while the other
+    // CTAs of the SM keep the memory system full of spectrum stores, and a load then takes thousands
+    // of cycles — a load / store / load loop would pay that latency once per trip.  The odd samples at
+    // either end are fetched by the last warp alongside its pairs.
+    const int last = head + 2 * pairs;           // first sample after the aligned middle
+    const bool odd_head = head && tid == nthreads - 1;
+    const bool odd_tail = tid == nthreads - 2 && last < n;
+    double e = 0.0;
+    if (odd_head && n > 0) e = g[0];
+    if (odd_tail) e = g[last];
+    constexpr int kInFlight = 4;
+    for (int j0 = tid; j0 < pairs; j0 += kInFlight * nthreads) {
+        double2 v[kInFlight];
+#pragma unroll
+        for (int u = 0; u < kInFlight; u++) {
+            const int j = j0 + u * nthreads;
+            v[u] = j < pairs ? g2[j] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < kInFlight; u++) {
+            const int j = j0 + u * nthreads;
+            if (j < pairs) { x[head + 2 * j] = v[u].x; x[head + 2 * j + 1] = v[u].y; }
+        }
     }
-    for (int i = head + 2 * pairs + tid; i < count; i += nthreads) x[i] = (i < n) ? g[i] : 0.0;
+    if (odd_head) x[0] = e;
+    if (odd_tail) x[last] = e;
+    for (int i = (last < n ? last + 1 : last) + tid; i < count; i += nthreads) x[i] = 0.0;   // beyond the series
+}
+
+// The tiles of a series overlap in all but their newest T * hop samples, and those have been read by
+// nobody when the tile starts: its staging would wait for a DRAM read that queues behind the spectrum
+// stores of the whole chip (several thousand cycles).  So every CTA first asks L2 for the new samples
+// of the tile `ahead` tiles further on, which some SM will start about a wave later.
+__device__ __forceinline__ void prefetch_future_tile(const double* __restrict__ series, int64_t series_len,
+                                                     int64_t first_new, int count, int tid) {
+    const int64_t i = first_new + (int64_t)tid * 16;                 // one 128-byte line per thread
+    if (tid * 16 < count + 16 && i < series_len)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(series + i));
 }
 
 // Host side: true the first time a kernel instantiation is launched on the current device (the

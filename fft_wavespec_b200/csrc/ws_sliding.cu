@@ -32,6 +32,10 @@
 #include "ws_series.h"
 #include "ws_sliding_core.cuh"
 
+#ifndef WS_TW_SMEM
+#define WS_TW_SMEM 1
+#endif
+
 namespace ws {
 
 using ws_slide::Plan;
@@ -57,6 +61,7 @@ struct SlideLayout {
     int ring_off;       // staged: S rings of `ring_slots` spectrum rows (N/2 double2 each)
     int ring_slots;
     int special_off;    // staged: [T][8] bins of the packed slot 0 (multiples of N/16)
+    int tw_off;         // overlap: the N/4 twiddles every pass of the tile uses, staged beside the samples
     int total_bytes;
 };
 
@@ -135,6 +140,8 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     const int nvalid = (int)((wend - w0) < pl.T ? (wend - w0) : pl.T);
 
     // 1. stage the tile (+ halo); beyond the series the samples only feed windows that are never stored
+    if (p.prefetch_tiles > 0)
+        prefetch_future_tile(src, p.series_len, w0 + (int64_t)p.prefetch_tiles * pl.T + (N - 1), pl.T, tid);
     {
         const int64_t left = (int64_t)p.series_len - w0;
         stage_samples(src + w0, pl.x_len, left > pl.x_len ? pl.x_len : (int)left, x, tid, NT);
@@ -241,17 +248,34 @@ sliding_overlap_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     const double* src = p.series + (int64_t)s * p.series_stride;
     const int nvalid = (int)((wend - w0) < pl.T ? (wend - w0) : pl.T);
 
+    // Every twiddle the tile needs is one of the first N/4 table entries (all passes use W_N^j with
+    // j < N/4): they are fetched together with the samples, so that the passes never wait for the
+    // memory system again — a global load issued under the other CTAs' spectrum stores takes
+    // thousands of cycles, and there were five of them in a row between here and the top pass.
+    double2* tws = reinterpret_cast<double2*>(smem_raw + lay.tw_off);
+    const double2* twu = WS_TW_SMEM ? tws : p.tw;
+    if (p.prefetch_tiles > 0)
+        prefetch_future_tile(src, p.series_len, w0 + (int64_t)p.prefetch_tiles * pl.T + (N - 1), pl.T, tid);
     {
+        double2 twv[(N / 4 + kSlideThreads - 1) / kSlideThreads];
+#pragma unroll
+        for (int u = 0; u < (N / 4 + kSlideThreads - 1) / kSlideThreads; u++)
+            if (WS_TW_SMEM && tid + u * kSlideThreads < N / 4) twv[u] = p.tw[tid + u * kSlideThreads];
         const int64_t left = (int64_t)p.series_len - w0;
         stage_samples(src + w0, pl.x_len, left > pl.x_len ? pl.x_len : (int)left, x, tid, kSlideThreads);
+#pragma unroll
+        for (int u = 0; u < (N / 4 + kSlideThreads - 1) / kSlideThreads; u++)
+            if (WS_TW_SMEM && tid + u * kSlideThreads < N / 4) tws[tid + u * kSlideThreads] = twv[u];
     }
     __syncthreads();
-    ws_slide::bottom_level(tid, kSlideThreads, x, pl, p.tw, arena);
+    constexpr int NST = ws_slide::LevelsOf<N>::nst;          // the plan's top is 3 here: compile-time level structure
+    ws_slide::bottom_level<NST, ws_slide::LevelsOf<N>::Lb>(tid, kSlideThreads, x, pl, twu, arena);
     __syncthreads();
-    for (int i = pl.nst; i >= 2; i--) {
+#pragma unroll
+    for (int i = NST; i >= 2; i--) {
         ws_slide::SmemSink sink{arena + pl.off[i - 1], pl.stride[i - 1]};
         ws_slide::direct_pass(tid, kSlideThreads, arena + pl.off[i], pl.stride[i], pl.Q[i], 1 << pl.lev[i - 1],
-                              pl.P[i - 1], p.tw, pl.N, pl.lev[i - 1], sink);
+                              pl.P[i - 1], twu, pl.N, pl.lev[i - 1], sink);
         __syncthreads();
     }
 
@@ -272,7 +296,7 @@ sliding_overlap_kernel(const Params p, const Plan pl, const SlideLayout lay) {
         const bool active = tid < pl.S * gen;
         const int sub = active ? tid / gen : 0;
         const int k = active ? 1 + tid - sub * gen : 1;
-        ws_slide::chain_single<N>(active, k, sub * per, per, lvl3, p.tw, top, [&](int it) {
+        ws_slide::chain_single<N>(active, k, sub * per, per, lvl3, twu, top, [&](int it) {
             __threadfence_block();               // the group's captured bins before the arrival
             __syncwarp();
             named_arrive(1 + it, bar_count);
@@ -285,7 +309,7 @@ sliding_overlap_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     const int ncons = kSlideThreads - nprod;
     const int ctid = tid - nprod;
     const int cw = ctid >> 5, ncw = ncons >> 5;
-    ws_slide::special_pass<N>(ctid, ncons, lvl3, pl.T, p.tw, top);
+    ws_slide::special_pass<N>(ctid, ncons, lvl3, pl.T, twu, top);
     named_sync(15, ncons);
     const int64_t gw_tile = (int64_t)s * p.nwin + w0;
     double* stage = reinterpret_cast<double*>(smem_raw + lay.stage_off) + cw * 512;
@@ -603,10 +627,13 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
             const int stage_bytes = (kSlideThreads - ((pl.S * gen + 31) & ~31)) / 32 * 512 * 8;   // per consumer warp
             int so = 0, total = xo + xb_bytes;
             if (stage_bytes > below3) { so = (xo + xb_bytes + 15) & ~15; total = so + stage_bytes; }
+            const int two = (total + 15) & ~15;          // twiddles: live from staging to the end of the top pass
+            total = two + (p.N / 4) * 16;
             if (total <= 113 * 1024) {                   // keep two CTAs per SM
                 lay.overlap = 1;
                 lay.xb_off = xo;
                 lay.stage_off = so;
+                lay.tw_off = two;
                 end = total;
             }
         }
@@ -699,6 +726,12 @@ cudaError_t launch_sliding_shared(Params p, cudaStream_t stream, const char** wh
     if (!pick_plan(p, pl, lay)) return cudaErrorInvalidValue;
     if (which && lay.overlap && !p.band_buf) *which = lay.staged ? "sliding_staged" : "sliding_overlap";
     p.tile_windows = pl.T;
+    {
+        // tiles ahead whose new samples a CTA pulls into L2: about one wave of resident CTAs
+        static int pf = -2;
+        if (pf == -2) { const char* e = getenv("WAVESPEC_PREFETCH"); pf = e ? atoi(e) : 296; }
+        p.prefetch_tiles = pf;
+    }
     switch (p.N) {
         case 256: return launch_n<256>(p, pl, lay, stream);
         case 512: return launch_n<512>(p, pl, lay, stream);

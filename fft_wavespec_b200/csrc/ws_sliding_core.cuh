@@ -59,7 +59,9 @@ struct Plan {
     int arena_slots;  // total double2 slots of the vector arena
 };
 
-WS_HD int top_stride(int q) { return q >= 64 ? q : q + (q >> 3 ? (q >> 3) : 1); }
+// odd, so that the lanes of a warp that hold the same slot of consecutive positions (direct_pass, the
+// bottom level) never share a bank group
+WS_HD int top_stride(int q) { return q + 1; }
 
 WS_HD bool plan_make(Plan& pl, int N, int T, int S, int top = 3) {
     pl.N = N;
@@ -82,10 +84,7 @@ WS_HD bool plan_make(Plan& pl, int N, int T, int S, int top = 3) {
     for (int i = 0; i <= pl.nst; i++) {
         pl.Q[i] = N >> (pl.lev[i] + 1);
         pl.P[i] = T + (1 << pl.lev[i]) - 1;
-        // pad so that the 8 lanes of a quarter warp never share a bank group when they write
-        // different positions (a writer pass has Q_in = q/8 slots per residue)
-        int q = pl.Q[i];
-        pl.stride[i] = (i == pl.nst && i != 1) ? q + 1 : top_stride(q);
+        pl.stride[i] = top_stride(pl.Q[i]);
     }
     // arena order: deepest level first, the level read by the top pass last, so that the epilogue
     // buffers can reuse everything below it while the top pass still reads it
@@ -212,31 +211,31 @@ WS_HD void radix8_special(const double2 I[8], const Tw4s& t, double2 o[8]) {
     bfly(c3[0], c3[1], t.wc, o[6], o[7]);
 }
 
-// ---- chain-free pass (lower levels): one work item per (position, slot) -------------------------
+// ---- chain-free pass (lower levels): one work item per (slot, position) -------------------------
 // Sink: put(pos, idx, value).  12 butterflies per general item instead of the chain's 7, but every
 // item is independent, so the whole CTA works on it (the lower levels are ~12% of the arithmetic).
+// Items are numbered position-fastest: the lanes of a warp hold the SAME slot of consecutive
+// positions, so with the odd position strides every shared-memory access of the pass is free of
+// bank conflicts and the twiddles are warp-uniform (broadcast) loads; the packed slot 0 is one more
+// row of items, so that the pass is a single sweep over n_out * Q items.
 template <class Sink>
 WS_HD void direct_pass(int tid, int nthreads, const double2* in, int in_stride, int Q, int D, int n_out,
                        const double2* tw, int N, int s_level, Sink& sink) {
     const int L = N >> s_level;
-    const int gen = Q - 1;
-    for (int item = tid; item < n_out * gen; item += nthreads) {
-        const int m = item / gen, k = 1 + item - m * gen;
-        const Tw7 t = load_tw7(tw, N, L, Q, k);
+    for (int item = tid; item < n_out * Q; item += nthreads) {
+        const int k = item / n_out, m = item - k * n_out;
         double2 I[8], o[8];
         int idx[8];
         for (int j = 0; j < 8; j++) I[j] = in[(m + j * D) * in_stride + k];
-        radix8_general(I, t, o);
-        slot_index8(Q, k, idx);
-        for (int j = 0; j < 8; j++) sink.put(m, idx[j], o[j]);
-    }
-    const Tw4s ts = load_tw4s(tw, N, L, Q);
-    for (int m = tid; m < n_out; m += nthreads) {
-        double2 I[8], o[8];
-        int idx[8];
-        for (int j = 0; j < 8; j++) I[j] = in[(m + j * D) * in_stride];
-        radix8_special(I, ts, o);
-        slot_index8_special(Q, idx);
+        if (k) {
+            const Tw7 t = load_tw7(tw, N, L, Q, k);
+            radix8_general(I, t, o);
+            slot_index8(Q, k, idx);
+        } else {
+            const Tw4s ts = load_tw4s(tw, N, L, Q);
+            radix8_special(I, ts, o);
+            slot_index8_special(Q, idx);
+        }
         for (int j = 0; j < 8; j++) sink.put(m, idx[j], o[j]);
     }
 }
@@ -272,7 +271,7 @@ WS_HD void bfly_alt(double2 A, double2 B, double2 w, double2& P, double2& R) {
 
 template <int N, int TOP = 3> struct TopGeomT {
     static constexpr int Q = N >> (TOP + 1);                          // slots of a vector at level TOP
-    static constexpr int stride = Q >= 64 ? Q : Q + ((Q >> 3) ? (Q >> 3) : 1);   // = Plan::stride[1]
+    static constexpr int stride = Q + 1;                             // = Plan::stride[1] = top_stride(Q)
 };
 template <int N> using TopGeom = TopGeomT<N, 3>;
 
@@ -476,14 +475,18 @@ WS_HD void chain_pass4(int tid, int nthreads, const double2* in, int T, int S, c
     }
 }
 
-// bottom level for all positions: one position per thread step
+// bottom level for all positions: one position per thread step.  A kernel templated on N passes
+// the stored-level count and the DFT length at compile time (NST, LB): no run-time indexing of the
+// Plan arrays, one SmallRdft instance instead of four.
+template <int NST = 0, int LB = 0>
 WS_HD void bottom_level(int tid, int nthreads, const double* x, const Plan& pl, const double2* tw,
                         double2* arena) {
-    const int i = pl.nst;
-    const int step = 1 << pl.sb;
+    const int i = NST ? NST : pl.nst;
+    const int step = 1 << pl.lev[i];
     double2* out = arena + pl.off[i];
     for (int p = tid; p < pl.P[i]; p += nthreads) {
         double2* o = out + (size_t)p * pl.stride[i];
+        if (LB) { SmallRdft<(LB ? LB : 2)>::run(x + p, step, tw, pl.N, o); continue; }
         switch (pl.Lb) {
             case 2: SmallRdft<2>::run(x + p, step, tw, pl.N, o); break;
             case 4: SmallRdft<4>::run(x + p, step, tw, pl.N, o); break;
@@ -492,6 +495,12 @@ WS_HD void bottom_level(int tid, int nthreads, const double* x, const Plan& pl, 
         }
     }
 }
+
+// stored levels and bottom DFT length of a window length, as plan_make derives them for top = 3
+template <int N> struct LevelsOf {
+    static constexpr int nst = (N >> 3) <= 16 ? 1 : ((N >> 6) <= 16 ? 2 : 3);
+    static constexpr int Lb = N >> (3 * nst);
+};
 
 struct SmemSink {
     double2* base; int stride;
