@@ -32,6 +32,9 @@
 #include "ws_series.h"
 #include "ws_sliding_core.cuh"
 
+#ifndef WS_BULK_STAGE
+#define WS_BULK_STAGE 1
+#endif
 #ifndef WS_TW_SMEM
 #define WS_TW_SMEM 1
 #endif
@@ -139,23 +142,56 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     const double* src = p.series + (int64_t)s * p.series_stride;
     const int nvalid = (int)((wend - w0) < pl.T ? (wend - w0) : pl.T);
 
-    // 1. stage the tile (+ halo); beyond the series the samples only feed windows that are never stored
+    // 1. stage the tile (+ halo); beyond the series the samples only feed windows that are never stored.
+    // The N/4 twiddles the passes use come along when the layout has room for them (see
+    // sliding_overlap_kernel): no pass waits for the memory system after this point.  Measured: the
+    // pure spectra writer at N <= 1024 — two chain warps per CTA, bound by the store stream alone — is
+    // 9-14 % SLOWER with the table and the compile-time level structure (1.80-1.90 against 1.65 ms per
+    // 1.2 M windows at N = 1024), every other instance 5-15 % faster; it keeps the plain form.
+    constexpr bool kLean = SPEC && CAP == 0 && N <= 1024;
     if (p.prefetch_tiles > 0)
         prefetch_future_tile(src, p.series_len, w0 + (int64_t)p.prefetch_tiles * pl.T + (N - 1), pl.T, tid);
-    {
+    const double2* twu = p.tw;
+    if constexpr (kLean) {
         const int64_t left = (int64_t)p.series_len - w0;
         stage_samples(src + w0, pl.x_len, left > pl.x_len ? pl.x_len : (int)left, x, tid, NT);
-    }
-    __syncthreads();
-    // 2. deepest level straight from the samples
-    ws_slide::bottom_level(tid, NT, x, pl, p.tw, arena);
-    __syncthreads();
-    // 3. chain-free radix-8 passes down to level 3
-    for (int i = pl.nst; i >= 2; i--) {
-        ws_slide::SmemSink sink{arena + pl.off[i - 1], pl.stride[i - 1]};
-        ws_slide::direct_pass(tid, NT, arena + pl.off[i], pl.stride[i], pl.Q[i], 1 << pl.lev[i - 1],
-                              pl.P[i - 1], p.tw, pl.N, pl.lev[i - 1], sink);
         __syncthreads();
+        ws_slide::bottom_level(tid, NT, x, pl, twu, arena);
+        __syncthreads();
+        for (int i = pl.nst; i >= 2; i--) {
+            ws_slide::SmemSink sink{arena + pl.off[i - 1], pl.stride[i - 1]};
+            ws_slide::direct_pass(tid, NT, arena + pl.off[i], pl.stride[i], pl.Q[i], 1 << pl.lev[i - 1],
+                                  pl.P[i - 1], twu, pl.N, pl.lev[i - 1], sink);
+            __syncthreads();
+        }
+    } else {
+        constexpr int TWN = (N / 4 + NT - 1) / NT;
+        double2 twv[TWN];
+        if (lay.tw_off) {
+#pragma unroll
+            for (int u = 0; u < TWN; u++) if (tid + u * NT < N / 4) twv[u] = p.tw[tid + u * NT];
+        }
+        const int64_t left = (int64_t)p.series_len - w0;
+        stage_samples(src + w0, pl.x_len, left > pl.x_len ? pl.x_len : (int)left, x, tid, NT);
+        if (lay.tw_off) {
+            double2* tws = reinterpret_cast<double2*>(smem_raw + lay.tw_off);
+#pragma unroll
+            for (int u = 0; u < TWN; u++) if (tid + u * NT < N / 4) tws[tid + u * NT] = twv[u];
+            twu = tws;
+        }
+        __syncthreads();
+        // 2. deepest level straight from the samples
+        constexpr int NST = ws_slide::LevelsOf<N, TOP>::nst;      // compile-time level structure
+        ws_slide::bottom_level<NST, ws_slide::LevelsOf<N, TOP>::Lb>(tid, NT, x, pl, twu, arena);
+        __syncthreads();
+        // 3. chain-free radix-8 passes down to level 3
+#pragma unroll
+        for (int i = NST; i >= 2; i--) {
+            ws_slide::SmemSink sink{arena + pl.off[i - 1], pl.stride[i - 1]};
+            ws_slide::direct_pass(tid, NT, arena + pl.off[i], pl.stride[i], pl.Q[i], 1 << pl.lev[i - 1],
+                                  pl.P[i - 1], twu, pl.N, pl.lev[i - 1], sink);
+            __syncthreads();
+        }
     }
     // 4. top pass: level 3 -> full spectra, streamed to HBM
     const bool want_sel = CAP == 1;
@@ -168,8 +204,8 @@ sliding_shared_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     if (p.select == 1 && top.lo < 1) top.lo = 1;
     if (lay.band <= 0) { top.lo = 1; top.hi = 0; }      // empty band: capture nothing
     top.nvalid = nvalid;
-    if (TOP == 3) ws_slide::chain_pass<N>(tid, NT, arena + pl.off[1], pl.T, pl.S, p.tw, top);
-    else ws_slide::chain_pass4<N>(tid, NT, arena + pl.off[1], pl.T, pl.S, p.tw, top);
+    if (TOP == 3) ws_slide::chain_pass<N>(tid, NT, arena + pl.off[1], pl.T, pl.S, twu, top);
+    else ws_slide::chain_pass4<N>(tid, NT, arena + pl.off[1], pl.T, pl.S, twu, top);
     if (!want_sel) return;
     __syncthreads();
     // 5. selection + rows
@@ -256,6 +292,40 @@ sliding_overlap_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     const double2* twu = WS_TW_SMEM ? tws : p.tw;
     if (p.prefetch_tiles > 0)
         prefetch_future_tile(src, p.series_len, w0 + (int64_t)p.prefetch_tiles * pl.T + (N - 1), pl.T, tid);
+#if WS_BULK_STAGE
+    // The tile and the twiddles arrive through the bulk-copy engine (cp.async.bulk + mbarrier): an
+    // ld.global issued here would queue behind the spectrum stores the SM's other CTA has in flight.
+    // The engine needs 16-byte aligned addresses and sizes: the sample array is shifted by one slot when
+    // the tile starts on an odd sample, the copy may take one sample past the tile when the series has
+    // it, and whatever is left at either end (odd first sample, end of the series) moves by plain loads.
+    {
+        const double* g = src + w0;
+        const int64_t left = (int64_t)p.series_len - w0;
+        const int head = (int)((reinterpret_cast<unsigned long long>(g) >> 3) & 1ull);
+        x += head;                                                   // x[head] is 16-byte aligned
+        const int want = (pl.x_len - head + 1) & ~1;
+        const int64_t avail = left - head;
+        const int nb = avail >= want ? want : (avail > 0 ? (int)(avail & ~1LL) : 0);
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(smem_raw + lay.tw_off + (N / 4) * 16);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nb * 8 + (N / 4) * 16) : "memory");
+            if (nb > 0)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"((unsigned)__cvta_generic_to_shared(x + head)), "l"(g + head), "r"(nb * 8), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((unsigned)__cvta_generic_to_shared(tws)), "l"(p.tw), "r"((N / 4) * 16), "r"(bar) : "memory");
+        }
+        if (head && tid == 32) x[0] = left > 0 ? g[0] : 0.0;
+        for (int i = head + nb + tid; i < pl.x_len; i += kSlideThreads) x[i] = i < left ? g[i] : 0.0;
+        __syncthreads();                                             // the barrier is initialised for everybody
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar) : "memory");
+    }
+#else
     {
         double2 twv[(N / 4 + kSlideThreads - 1) / kSlideThreads];
 #pragma unroll
@@ -268,6 +338,7 @@ sliding_overlap_kernel(const Params p, const Plan pl, const SlideLayout lay) {
             if (WS_TW_SMEM && tid + u * kSlideThreads < N / 4) tws[tid + u * kSlideThreads] = twv[u];
     }
     __syncthreads();
+#endif
     constexpr int NST = ws_slide::LevelsOf<N>::nst;          // the plan's top is 3 here: compile-time level structure
     ws_slide::bottom_level<NST, ws_slide::LevelsOf<N>::Lb>(tid, kSlideThreads, x, pl, twu, arena);
     __syncthreads();
@@ -568,7 +639,7 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
     if (p.select == 1 && lo < 1) lo = 1;
     const bool sel = (p.bins || p.rows || p.waves || p.contrib) && !p.band_buf;
     lay.band = ((sel || p.band_buf) && hi >= lo) ? hi - lo + 1 : 0;
-    lay.x_doubles = (pl.x_len + 1) & ~1;
+    lay.x_doubles = (pl.x_len + 4) & ~1;        // room for the 16-byte aligned bulk staging (one sample of shift, one of over-read)
     lay.arena_off = lay.x_doubles * 8;
     const int below3 = lay.arena_off + pl.off[1] * 16;               // bytes below the level-3 array
     const int work_end = lay.arena_off + pl.arena_slots * 16;
@@ -628,7 +699,7 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
             int so = 0, total = xo + xb_bytes;
             if (stage_bytes > below3) { so = (xo + xb_bytes + 15) & ~15; total = so + stage_bytes; }
             const int two = (total + 15) & ~15;          // twiddles: live from staging to the end of the top pass
-            total = two + (p.N / 4) * 16;
+            total = two + (p.N / 4) * 16 + 16;           // + the mbarrier of the bulk staging
             if (total <= 113 * 1024) {                   // keep two CTAs per SM
                 lay.overlap = 1;
                 lay.xb_off = xo;
@@ -640,6 +711,15 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
     }
     lay.total_bytes = end > work_end ? end : work_end;
     lay.total_bytes = (lay.total_bytes + 15) & ~15;
+    if (!lay.overlap) {
+        // twiddle table behind everything else, unless it would cost a resident CTA (or not fit at all)
+        const int with_tw = lay.total_bytes + (p.N / 4) * 16;
+        const int cap = lay.total_bytes <= 113 * 1024 ? 113 * 1024 : 232448;
+        static int want_tw = -1;
+        if (want_tw < 0) { const char* e = getenv("WAVESPEC_TWS"); want_tw = (e && e[0] == '0') ? 0 : 1; }
+        const bool lean = p.spectra && !sel && !p.band_buf && p.N <= 1024;      // kLean instance of the kernel
+        if (want_tw && !lean && lay.total_bytes > 0 && with_tw <= cap) { lay.tw_off = lay.total_bytes; lay.total_bytes = with_tw; }
+    }
     return lay.total_bytes <= 232448;
 }
 

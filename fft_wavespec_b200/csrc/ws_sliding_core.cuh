@@ -497,9 +497,9 @@ WS_HD void bottom_level(int tid, int nthreads, const double* x, const Plan& pl, 
 }
 
 // stored levels and bottom DFT length of a window length, as plan_make derives them for top = 3
-template <int N> struct LevelsOf {
-    static constexpr int nst = (N >> 3) <= 16 ? 1 : ((N >> 6) <= 16 ? 2 : 3);
-    static constexpr int Lb = N >> (3 * nst);
+template <int N, int TOP = 3> struct LevelsOf {
+    static constexpr int nst = (N >> TOP) <= 16 ? 1 : ((N >> (TOP + 3)) <= 16 ? 2 : 3);
+    static constexpr int Lb = N >> (TOP + 3 * (nst - 1));
 };
 
 struct SmemSink {
