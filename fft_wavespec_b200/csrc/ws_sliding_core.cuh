@@ -250,7 +250,7 @@ WS_HD void direct_pass(int tid, int nthreads, const double2* in, int in_stride, 
 // the other three follow from  W^{L/4 - j} = -i conj(W^j)  (bfly_alt).  The loop is unrolled by 4 so
 // the three register queues (inputs: 4 deep, level 2: 2 deep, level 1: 2 deep) rotate by renaming.
 //
-// Sink: bind(k) once per chain; begin(m) once per window; put<J>(value), J = slot_index8 order;
+// Sink: bind(k, m0) once per chain (the windows follow consecutively from m0); begin(m) once per window; put<J>(value), J = slot_index8 order;
 //       put0(m, idx, value) for the bins that come from the packed slot 0.
 template <int J> struct SlotOfs;    // C_J in units of Q, and the sign of k
 template <> struct SlotOfs<0> { static constexpr int c = 0, sgn = +1; };
@@ -307,7 +307,7 @@ WS_HD void chain_single(bool active, int k, int m0, int per, const double2* in, 
     const double2 w0a = tw[k];               // W_N^k
     const double2 w0c = tw[2 * Q - k];       // W_N^{2Q-k}
     const double2* src = in + k;
-    sink.bind(k);
+    sink.bind(k, m0);
     double2 qa, qb, qc, qd;                  // inputs I_{m+3..m+6}
     double2 eP, eR, oP, oR;                  // F2(m+1), F2(m+2)
     double2 ha[4], hb[4];                    // F1(m) / F1(m+1), alternating
@@ -348,7 +348,7 @@ WS_HD void chain_single_stepwise(bool active, int k, int m0, int per, const doub
     const double2 w0a = tw[k];
     const double2 w0c = tw[2 * Q - k];
     const double2* src = in + k;
-    sink.bind(k);
+    sink.bind(k, m0);
     double2 qa, qb, qc, qd;
     double2 eP, eR, oP, oR;
     double2 ha[4], hb[4];
@@ -443,7 +443,7 @@ WS_HD void chain_pass4(int tid, int nthreads, const double2* in, int T, int S, c
         const double2 w0 = tw[k];                // W_N^k
         const double2* src = in + k;
         const int m0 = sub * per;
-        sink.bind(k);
+        sink.bind(k, m0);
         double2 qa, qb;                          // F2(m+1), F2(m+2)
         double2 ha[2], hb[2];                    // F1(m) / F1(m+1), alternating
         {

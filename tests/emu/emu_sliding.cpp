@@ -16,7 +16,7 @@ template <int N, int TOP>
 struct GlobalSink {
     double* out; int64_t w0, nwin;
     int k; int pos;
-    void bind(int kk) { k = kk; }
+    void bind(int kk, int) { k = kk; }
     void begin(int p) { pos = p; }
     template <int J> void put(double2 v) {
         if (TOP == 3) store(pos, SlotOfs<J>::c * (N / 16) + SlotOfs<J>::sgn * k, v);
@@ -100,7 +100,7 @@ struct EmuStageSink {
     double2* rows; int* hits; const double2* special;
     int k, kk;
     double2* slot; int* hslot;
-    void bind(int k_) { k = k_; }
+    void bind(int k_, int) { k = k_; }
     void begin(int m) { slot = rows + (size_t)m * N2; hslot = hits + (size_t)m * N2; }
     template <int J> void put(double2 v) {
         const int idx = SlotOfs<J>::c * Q + SlotOfs<J>::sgn * k;
