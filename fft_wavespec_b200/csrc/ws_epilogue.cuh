@@ -35,6 +35,46 @@ __device__ __forceinline__ void warp_argbest(double& p, int& pos) {
     }
 }
 
+// Top-K of a wide band (more entries than the lanes can hold in registers) in ONE pass over shared
+// memory: every lane walks its entries pw[lane], pw[lane + 32], .. in ascending order and keeps its C
+// best in a sorted register list (strict '>' on insertion: an equal power met later never gets ahead
+// of the earlier, lower bin); then K rounds of a warp argmax over the list heads, the winning lane
+// popping its head.  A lane can own at most K of the K winners, so C >= K makes the result exactly what
+// K scans of the whole band give.  NaN powers never enter a list.  Lane r returns winner r.
+template <int C>
+__device__ __forceinline__ void warp_wide_topk(const double* pw, int n, int K, int lane, int& my_pos, double& my_pow) {
+    double v[C];
+    int e[C];
+#pragma unroll
+    for (int j = 0; j < C; j++) { v[j] = -1.0; e[j] = 0x7fffffff; }
+    for (int i = lane; i < n; i += 32) {
+        const double q = pw[i];
+        if (q > v[C - 1]) {
+            bool placed = false;
+#pragma unroll
+            for (int j = C - 1; j >= 1; j--) {
+                if (!placed) {
+                    if (q > v[j - 1]) { v[j] = v[j - 1]; e[j] = e[j - 1]; }
+                    else { v[j] = q; e[j] = i; placed = true; }
+                }
+            }
+            if (!placed) { v[0] = q; e[0] = i; }
+        }
+    }
+    for (int r = 0; r < K; r++) {
+        double bp = v[0]; int bpos = e[0];
+        if (!(bp >= 0.0)) { bp = -1.0; bpos = 0x7fffffff; }
+        warp_argbest(bp, bpos);
+        if (bpos == 0x7fffffff) break;                  // band exhausted: remaining slots stay absent
+        if (bpos == e[0]) {
+#pragma unroll
+            for (int j = 0; j + 1 < C; j++) { v[j] = v[j + 1]; e[j] = e[j + 1]; }
+            v[C - 1] = -1.0; e[C - 1] = 0x7fffffff;
+        }
+        if (lane == r) { my_pos = bpos; my_pow = bp; }
+    }
+}
+
 // pw   : shared, powers of this window indexed by bin; only [band_lo, band_hi] is touched
 //        (destroyed: selected entries are overwritten)
 // getX : bin -> complex value of this window (called for the K selected bins only)
@@ -104,6 +144,12 @@ __device__ __forceinline__ void warp_select_emit_x(const Params& p, double* pw, 
             for (int i = 0; i < 4; i++) if (bpos == bb[i]) v[i] = -2.0;
             if (lane == r) { my_bin = bpos; my_pow = bp; }
         }
+    } else if (K <= 8) {
+        // wide bands (config 5: 435 bins at N = 4096 / 9-200): one pass, per-lane register lists
+        int pos = -1;
+        if (K <= 4) warp_wide_topk<4>(pw + lo, hi - lo + 1, K, lane, pos, my_pow);
+        else warp_wide_topk<8>(pw + lo, hi - lo + 1, K, lane, pos, my_pow);
+        if (pos >= 0) my_bin = lo + pos;
     } else {
         for (int r = 0; r < K; r++) {
             double bp = -1.0; int bpos = 0x7fffffff;
@@ -266,6 +312,11 @@ __device__ __forceinline__ void warp_select_emit_batch(const Params& p, double* 
         double* pwb = pw + g * band;
         if (live) for (int e = l; e < band; e += Lg) bsum += pwb[e];
         for (int m = Lg >> 1; m >= 1; m >>= 1) bsum += shfl_xor_d(bsum, m);
+        if (Lg == 32 && K <= 8) {
+            // one window per warp, wide band: one pass with per-lane register lists
+            if (K <= 4) warp_wide_topk<4>(pwb, live ? band : 0, K, lane, my_pos, my_pow);
+            else warp_wide_topk<8>(pwb, live ? band : 0, K, lane, my_pos, my_pow);
+        } else
         for (int r = 0; r < K; r++) {
             double bp = -1.0; int bpos = 0x7fffffff;
             // ascending scan inside a lane: an equal power met later never displaces the earlier

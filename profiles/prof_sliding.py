@@ -1,5 +1,5 @@
 """Small driver for ncu: launches the sliding kernel in three output modes (2 launches each):
-spectra+rows, spectra only, rows only.  Usage: python profiles/prof_sliding.py [N] [series] [bars]"""
+spectra+rows, spectra only, rows only.  Usage: python profiles/prof_sliding.py [N] [series] [bars] [top_k] [min_period]"""
 import os
 import sys
 
@@ -12,8 +12,9 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 300000
 assert bridge.gpu_init(0, 2) == 0
-K = 8
-cfg = bridge.default_cfg(N, top_k=K, min_period=18.0, max_period=200.0)
+K = int(sys.argv[4]) if len(sys.argv) > 4 else 8
+MINP = float(sys.argv[5]) if len(sys.argv) > 5 else 18.0
+cfg = bridge.default_cfg(N, top_k=K, min_period=MINP, max_period=200.0)
 nwin = T - N + 1
 d = torch.from_numpy(synth.random_walk_batch(0, S, T)).cuda()
 spec = torch.empty((S, nwin, N), dtype=torch.float64, device="cuda")

@@ -787,6 +787,25 @@ def test_warp_kernel_many_series_rows_only(br, oracle):
         check_planes(br, {k: (v[i] if v is not None else None) for k, v in got.items()}, ref, cfg)
 
 
+@pytest.mark.parametrize("top_k", [3, 4, 8, 12])
+@pytest.mark.parametrize("n", [1024, 4096])
+def test_sliding_kernel_wide_band_selection_with_ties(br, oracle, n, top_k):
+    """Bands wider than the lanes' register candidates (config 5: 435 bins): top_k <= 8 takes the one-pass
+    per-lane lists (ws_epilogue.cuh::warp_wide_topk), larger top_k the K scans; coarse quantisation and a
+    flat stretch force equal powers, which must resolve to the lower bin."""
+    s = np.round(synth.random_walk(1234 + n, n + 90), 3)
+    s[n // 2:n // 2 + 400] = s[n // 2]
+    # the widest bands whose capture still fits the sliding kernels' shared memory (bins 1..292 / 1..455)
+    cfg = br.default_cfg(n, top_k=top_k, min_period=3.5 if n == 1024 else 9.0, max_period=1.0e9)
+    got, ref = run_both(br, oracle, s, cfg, br.OUT_BINS | br.OUT_ROWS | br.OUT_WAVES)
+    if top_k <= 8:                      # larger top_k may not fit the sliding kernels' shared memory at this band
+        assert br.last_kernel().startswith("sliding")
+    check_planes(br, got, ref, cfg)
+    flat = np.full(n + 40, 1.2345)
+    got, ref = run_both(br, oracle, flat, cfg, br.OUT_BINS)
+    assert np.array_equal(got["bins"], ref["bins"])
+
+
 # ---- producer / consumer sliding kernel vs the phase-ordered one --------------------------------
 @pytest.mark.parametrize("n,tile", [(1024, 40), (512, 64), (256, 128)])
 def test_overlap_kernel_ragged_tiles_against_oracle(br, oracle, n, tile):
