@@ -1,5 +1,6 @@
 // ws_runtime.cu — devices, coefficient tables and pools of the host runtime (see ws_runtime.h).
 #include "ws_runtime.h"
+#include "ws_warpfft_core.cuh"
 
 #include <cmath>
 #include <cstring>
@@ -106,6 +107,15 @@ int Device::get_twiddles(int N, const double2** out) {
         h[0] = 1.0; h[1] = 0.0;
         if (N >= 2) { h[2 * (N / 2)] = -1.0; h[2 * (N / 2) + 1] = 0.0; }
         if (N >= 4) { h[2 * (N / 4)] = 0.0; h[2 * (N / 4) + 1] = -1.0; h[2 * (3 * N / 4)] = 0.0; h[2 * (3 * N / 4) + 1] = 1.0; }
+        // behind the N entries: the per-pass blocks of the warp-per-window transforms (ws_warpfft_core.cuh)
+        int ln = 0;
+        while ((1 << ln) < N) ln++;
+        if ((1 << ln) == N && ln >= 4) {
+            const int extra = ws_wf::pass_twiddle_count(ln);
+            h.resize(2 * (size_t)(N + extra));
+            ws_wf::fill_pass_twiddles(ln, reinterpret_cast<const double2*>(h.data()),
+                                      reinterpret_cast<double2*>(h.data()) + N);
+        }
         std::unique_ptr<DeviceBuf> buf;
         int rc = upload_table(h, buf, "twiddle table");
         if (rc) return rc;

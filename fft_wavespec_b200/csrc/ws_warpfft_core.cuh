@@ -62,6 +62,17 @@ struct Geo {
         for (int q = 0; q <= p; q++) s /= radix(q);
         return s;
     }
+    // The twiddles of the radix-8 passes live BEHIND the N-entry table exp(-2 pi i m / N), one block per
+    // twiddled pass (stride S > 1) in pass order, each laid out [r - 1][i], r = 1..7, i < S, holding
+    // W_{8S}^{i r}: the lanes of a warp have consecutive i, so each of the seven loads of a butterfly
+    // is one contiguous run (4 L1 wavefronts per warp at S >= 32, a single line at S = 8) — gathering
+    // W^t, W^2t, W^4t from the N-entry table cost 56 wavefronts per warp in pass 0 at N = 1024 plus
+    // four complex products per butterfly, on a kernel whose L1 data pipe is 86 % busy (ncu).
+    static WF_HD constexpr int tw_off(int S) {             // offset of the block of the pass with stride S
+        int off = 0, s = M;
+        for (int q = 0; q < P8; q++) { s /= 8; if (s > S) off += 7 * s; }
+        return off;
+    }
     // position of output bin k after the last pass (digit reversal over the pass radices)
     static WF_HD int rev(int k) {
         int pos = 0, rem = k;
@@ -74,6 +85,26 @@ struct Geo {
         return pos;
     }
 };
+
+// Host side: number of pass-twiddle entries behind the N-entry table of an N = 2^LN transform, and
+// their values, taken from the table itself (entry [r - 1][i] of the pass with stride S is
+// tw[(N / 8S) i r]).  Mirrors Geo<LN>::tw_off for a run-time LN.
+inline int pass_twiddle_count(int LN) {
+    const int LM = LN - 1, P8 = LM / 3;
+    int s = 1 << LM, total = 0;
+    for (int q = 0; q < P8; q++) { s /= 8; if (s > 1) total += 7 * s; }
+    return total;
+}
+inline void fill_pass_twiddles(int LN, const double2* tw, double2* out) {
+    const int N = 1 << LN, LM = LN - 1, P8 = LM / 3;
+    int s = 1 << LM;
+    for (int q = 0; q < P8; q++) {
+        s /= 8;
+        if (s <= 1) continue;
+        for (int r = 1; r < 8; r++)
+            for (int i = 0; i < s; i++) *out++ = tw[(N / (8 * s)) * i * r];
+    }
+}
 
 // conflict-free placement (see header)
 WF_HD constexpr int swz(int x) { return x ^ ((x >> 3) & 7) ^ ((x >> 6) & 7) ^ ((x >> 9) & 7); }
@@ -127,13 +158,11 @@ WF_HD void dif_pass(int lane, Load load, double2* Z, const double2* tw) {
         else if (R == 4) bfly4(a);
         else { double2 x0 = a[0], x1 = a[1]; a[0] = c_add(x0, x1); a[1] = c_sub(x0, x1); }
         if (S > 1) {
-            // only radix-8 passes carry twiddles (the short pass is last): three table reads,
-            // the other four powers are products
-            const int t = (G::N / (R * S)) * i;
-            const double2 w1 = ld_tw(tw + t), w2 = ld_tw(tw + 2 * t), w4 = ld_tw(tw + 4 * t);
-            const double2 w3 = c_mul(w1, w2), w5 = c_mul(w1, w4), w6 = c_mul(w2, w4), w7 = c_mul(w3, w4);
-            a[1] = c_mul(a[1], w1); a[2] = c_mul(a[2], w2); a[3] = c_mul(a[3], w3); a[4] = c_mul(a[4], w4);
-            if (R == 8) { a[5] = c_mul(a[5], w5); a[6] = c_mul(a[6], w6); a[7] = c_mul(a[7], w7); }
+            // only radix-8 passes carry twiddles (the short pass is last): seven exact table values
+            // from the pass's own block (see Geo::tw_off)
+            const double2* tp = tw + G::N + G::tw_off(S) + i;
+#pragma unroll
+            for (int r = 1; r < R; r++) a[r] = c_mul(a[r], ld_tw(tp + (r - 1) * S));
         }
 #pragma unroll
         for (int r = 0; r < R; r++) Z[sb ^ swz(r * S)] = a[r];

@@ -16,11 +16,12 @@ namespace {
 template <int LN>
 int run(const double* v, double* out) {
     typedef Geo<LN> G;
-    std::vector<double2> tw(G::N);
+    std::vector<double2> tw(G::N + pass_twiddle_count(LN));
     for (int m = 0; m < G::N; m++) {
         long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)G::N;
         tw[m] = make_double2((double)cosl(a), (double)sinl(a));
     }
+    fill_pass_twiddles(LN, tw.data(), tw.data() + G::N);
     std::vector<double2> Z(G::M, make_double2(NAN, NAN));
     auto load = [&](int m) { return make_double2(v[2 * m], v[2 * m + 1]); };
     for (int lane = 0; lane < 32; lane++)
@@ -98,11 +99,12 @@ int conflicts(int* gather_worst) {
 template <int LN>
 int run_inverse(const double* spec, const unsigned char* keep, double* out) {
     typedef Geo<LN> G;
-    std::vector<double2> tw(G::N);
+    std::vector<double2> tw(G::N + pass_twiddle_count(LN));
     for (int m = 0; m < G::N; m++) {
         long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)G::N;
         tw[m] = make_double2((double)cosl(a), (double)sinl(a));
     }
+    fill_pass_twiddles(LN, tw.data(), tw.data() + G::N);
     std::vector<double2> Z(G::M, make_double2(NAN, NAN));
     auto X = [&](int k) { return (keep && !keep[k]) ? make_double2(0.0, 0.0) : make_double2(spec[2 * k], spec[2 * k + 1]); };
     for (int lane = 0; lane < 32; lane++)
