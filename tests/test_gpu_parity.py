@@ -878,6 +878,21 @@ def test_median_price_feeds_the_pipeline(br, oracle):
     check_planes(br, got, ref, cfg)
 
 
+@pytest.mark.parametrize("n", [256, 1024, 4096])
+def test_sliding_kernels_odd_series_stride(br, oracle, n):
+    """Series of odd length packed back to back: every second series starts on an odd sample, so its
+    tiles take the shifted form of the 16-byte aligned bulk staging (and the split-at-the-boundary form
+    of the 128-bit loads), and the last tile of each series runs into the next one's samples."""
+    s = synth.random_walk_batch(4321 + n, 3, n + 151)
+    cfg = br.default_cfg(n, top_k=8 if n < 4096 else 4, min_period=18.0, max_period=200.0)
+    for outs in (br.OUT_SPECTRA | br.OUT_ROWS | br.OUT_BINS, br.OUT_ROWS | br.OUT_BINS, br.OUT_SPECTRA):
+        got = br.pipeline_host(s, cfg, outs)
+        assert br.last_kernel().startswith("sliding")
+        for i in range(s.shape[0]):
+            ref = oracle.pipeline_series(s[i], ocfg_from(oracle, cfg), outs)
+            check_planes(br, {k: (v[i] if v is not None else None) for k, v in got.items()}, ref, cfg)
+
+
 # ---- 8(e): one series split over GPUs by bar range ----------------------------------------------
 @pytest.mark.parametrize("n,plain", [(1024, True), (512, False)])
 def test_bar_range_split_reproduces_the_unsplit_series(br, n, plain):
