@@ -24,6 +24,7 @@
 // Reference quirk kept on purpose: when the worst sample is the first of a segment, PlaSplit
 // recurses on [s,s] and on the same [s,e] again (:462-467), appending single-point segments
 // until the budget `count + 2 <= max_segments` is exhausted.
+#include <cstdlib>
 #include "ws_common.cuh"
 #include "ws_series.h"
 
@@ -151,7 +152,9 @@ cudaError_t launch_pla(const double* series, int64_t series_stride, int32_t n_se
     // The walk is bound by the FP64 pipe, which eight warps per scheduler already fill.  An (unused)
     // dynamic shared-memory request of 27 KB caps the residency at 8 CTAs per SM: a launch then runs
     // in twice as many waves and its last, partly filled wave costs half as much.
-    pla_kernel<<<grid, kPlaThreads, 27 * 1024, stream>>>(series, series_stride, nwin, N, hop, max_segments, max_error,
+    static int smem_kb = -1;
+    if (smem_kb < 0) { const char* e = getenv("WAVESPEC_PLA_SMEM_KB"); smem_kb = e ? atoi(e) : 27; }
+    pla_kernel<<<grid, kPlaThreads, smem_kb * 1024, stream>>>(series, series_stride, nwin, N, hop, max_segments, max_error,
                                                  lines, seg_bounds, seg_counts, bounds_cap, overflow);
     return cudaGetLastError();
 }

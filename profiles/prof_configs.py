@@ -73,4 +73,6 @@ run("C3 tracker slots only", 2048, 16, 200000, TR, min_period=18.0, max_period=5
     trend_period=1024.0, window_type=br.WINDOW_BLACKMAN)
 run("C3 tracker + bins", 2048, 4, 100000, TR | B, min_period=18.0, max_period=52.0, detrend=br.DETREND_IIR,
     trend_period=1024.0, window_type=br.WINDOW_BLACKMAN)
+run("C3 tracker + bins (64 x 200k)", 2048, 64, 200000, TR | B, min_period=18.0, max_period=52.0, detrend=br.DETREND_IIR,
+    trend_period=1024.0, window_type=br.WINDOW_BLACKMAN)
 br.gpu_shutdown()
