@@ -6,7 +6,8 @@
 //   submit (caller's thread): bind the job to a device (round robin), upload the series on that
 //       device's upload stream and wait for the upload only — the caller may reuse its buffer as
 //       soon as submit returns (WaveSpecZZ_1.1.0-gpuopt.mq5:1313-1339) — then hand the job to the
-//       device's worker thread.
+//       device's worker thread.  Single-window jobs skip the upload: their window and their rows live
+//       in one pinned host block that the kernels address directly.
 //   worker: allocates the product from the stream-ordered pool and enqueues the kernels in window
 //       chunks, recording an event per chunk.
 //   try_get (any thread): never waits for the device.  The first poll "arms" the caller's buffer.
@@ -35,8 +36,8 @@ Job::~Job() {
     DeviceGuard guard(dev->index);
     if (copied) { cudaEventSynchronize(copied); cudaEventDestroy(copied); }   // nothing may land in a freed caller buffer
     if (h_rows) {
-        // the pinned rows of a single-window job are written by a copy on `st`: wait for it before the
-        // buffer goes back to the pool
+        // the pinned block of a single-window job is read and written by the kernels on `st`: wait for
+        // them before it goes back to the pool
         if (state.load() == kLaunched && !chunks.empty() && chunks.back().done) cudaEventSynchronize(chunks.back().done);
         else cudaStreamSynchronize(st);
         dev->pinned.put(h_rows, h_rows_bytes);
@@ -73,6 +74,32 @@ int submit_job(const double* series, int32_t series_len, const wavespec_pipeline
     job->product_elems = kind == kJobCacheRecord ? (int64_t)series_len * 20 : job->rows * c.row_stride;
     job->st = dev->pick_stream();
     job->cst = dev->pick_copy_stream();
+    if (kind == kJobWindow) {
+        // Single-window jobs (one per bar in the 1.1.0 live loop, up to InpAsyncDepth in flight) run
+        // zero-copy: one pinned block holds the rows, then the window; the kernels address it directly
+        // (cudaHostAlloc memory is mapped under UVA).  No device allocation, no copy commands, nothing
+        // to wait for in submit — the caller's buffer is free as soon as the memcpy returns.
+        const size_t rows_bytes = (((size_t)job->rows * c.row_stride * 8) + 255) & ~(size_t)255;
+        size_t got = 0;
+        job->h_rows = dev->pinned.get(rows_bytes + (size_t)series_len * 8, &got);
+        if (!job->h_rows) return fail(WAVESPEC_NO_MEM, "pinned block of a window job");
+        job->h_rows_bytes = got;
+        job->h_series = reinterpret_cast<double*>(static_cast<char*>(job->h_rows) + rows_bytes);
+        std::memcpy(job->h_series, series, (size_t)series_len * 8);
+        int64_t id;
+        {
+            std::lock_guard<std::mutex> lk(g_rt.mu);
+            id = g_rt.next_job++;
+            g_rt.jobs[id] = job;
+        }
+        {
+            std::lock_guard<std::mutex> lk(dev->qmu);
+            dev->queue.push_back(job);
+        }
+        dev->qcv.notify_one();
+        *job_id = id;
+        return WAVESPEC_OK;
+    }
     // upload: the device buffer is released (stream-ordered) on the job's compute stream, so it is
     // allocated there; the copy itself runs on the upload stream and never queues behind kernels
     WS_CUDA(job->d_series.alloc((size_t)series_len * 8, dev->h2d), "cudaMallocAsync(series)");
@@ -104,13 +131,25 @@ static int launch_job(Job& job) {
     Device& dev = *job.dev;
     const wavespec_pipeline_cfg& c = job.cfg;
     cudaStream_t st = job.st;
+    if (job.kind == kJobWindow) {
+        Planes out;
+        out.rows = static_cast<double*>(job.h_rows);
+        int rc = run_pipeline(dev, job.h_series, 1, job.series_len, &c, out, st, 0, job.nwin);
+        if (rc) return rc;
+        Chunk ch;
+        ch.off = 0; ch.elems = job.rows * c.row_stride;
+        WS_CUDA(cudaEventCreateWithFlags(&ch.done, cudaEventDisableTiming), "cudaEventCreate");
+        job.chunks.push_back(ch);
+        WS_CUDA(cudaEventRecord(ch.done, st), "cudaEventRecord(chunk)");
+        return WAVESPEC_OK;
+    }
     WS_CUDA(cudaStreamWaitEvent(st, job.h2d_done, 0), "cudaStreamWaitEvent(upload)");
     WS_CUDA(job.d_rows.alloc((size_t)job.rows * c.row_stride * 8, st), "cudaMallocAsync(rows)");
     if (job.kind == kJobCacheRecord)
         WS_CUDA(job.d_record.alloc((size_t)job.series_len * 20 * 8, st), "cudaMallocAsync(cache record)");
     job.d_product = job.kind == kJobCacheRecord ? job.d_record.as<double>() : job.d_rows.as<double>();
     const int64_t nwin = job.nwin;
-    const int64_t per = job.kind == kJobWindow ? nwin : chunk_windows();
+    const int64_t per = chunk_windows();
     Planes out;
     out.rows = job.d_rows.as<double>();
     for (int64_t wa = 0; wa < nwin; wa += per) {
@@ -129,14 +168,6 @@ static int launch_job(Job& job) {
             ch.off = b0 * 20; ch.elems = (b1 - b0) * 20;
         } else {
             ch.off = wa * c.top_k * c.row_stride; ch.elems = cn * c.top_k * c.row_stride;
-        }
-        if (job.kind == kJobWindow) {
-            size_t got = 0;
-            job.h_rows = dev.pinned.get((size_t)ch.elems * 8, &got);
-            if (!job.h_rows) return fail(WAVESPEC_NO_MEM, "pinned staging for the rows of a window job");
-            job.h_rows_bytes = got;
-            WS_CUDA(cudaMemcpyAsync(job.h_rows, job.d_rows.p, (size_t)ch.elems * 8, cudaMemcpyDeviceToHost, st),
-                    "cudaMemcpyAsync(rows)");
         }
         WS_CUDA(cudaEventCreateWithFlags(&ch.done, cudaEventDisableTiming), "cudaEventCreate");
         job.chunks.push_back(ch);

@@ -159,9 +159,11 @@ struct Job {
     size_t next_chunk = 0;            // pageable delivery: chunks already copied
     cudaEvent_t copied = nullptr;     // pinned delivery: fires when the last chunk has landed
     bool delivered = false;
-    // single-window jobs: rows land in a pinned host buffer owned by the job
+    // single-window jobs: one pinned host block owned by the job — the rows, then the window — that
+    // the kernels read and write directly (zero-copy)
     void* h_rows = nullptr;
     size_t h_rows_bytes = 0;
+    double* h_series = nullptr;
     ~Job();
 };
 
