@@ -65,6 +65,7 @@ struct SlideLayout {
     int ring_slots;
     int special_off;    // staged: [T][8] bins of the packed slot 0 (multiples of N/16)
     int tw_off;         // overlap: the N/4 twiddles every pass of the tile uses, staged beside the samples
+    int fastsel;        // overlap: 32-bit key selection 0 never, 1 always, 2 for a tile's last groups only
     int total_bytes;
 };
 
@@ -410,7 +411,8 @@ sliding_overlap_kernel(const Params p, const Plan pl, const SlideLayout lay) {
         const int b0 = seg * per + 4 * it;
         if (b0 < nvalid) {
             const int nb = (nvalid - b0) < 4 ? (nvalid - b0) : 4;
-            warp_select_emit_batch<8>(p, nullptr, top.xb + b0 * lay.band, lay.band, top.lo, 8, nb, gw_tile + b0, stage);
+            const bool fast = lay.fastsel == 1 || (lay.fastsel == 2 && it == iters - 1);
+            warp_select_emit_batch<8>(p, nullptr, top.xb + b0 * lay.band, lay.band, top.lo, 8, nb, gw_tile + b0, stage, fast);
         }
     }
     if (dbg && (tid & 31) == 0) atomicMax((unsigned long long*)&dbg[3], (unsigned long long)clock64());
@@ -720,6 +722,12 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
             total = two + (p.N / 4) * 16 + 16;           // + the mbarrier of the bulk staging
             if (total <= 113 * 1024) {                   // keep two CTAs per SM
                 lay.overlap = 1;
+                // Measured (ms per 1.2 M windows, never / always / last groups only): N = 512 1.25 / 1.12 /
+                // 1.21, N = 1024 1.87 / 1.97 / 1.87.  Where the consumers are the slower side (N <= 512) the
+                // 32-bit keys pay; at N = 1024 the chains' store stream is the limit, consumers that issue
+                // faster only take issue slots from the chains, and a shorter tail buys nothing.
+                { static int fs = -1; if (fs < 0) { const char* e = getenv("WAVESPEC_FASTSEL"); fs = e ? atoi(e) : -1; }
+                  lay.fastsel = fs >= 0 ? fs : (p.N <= 512 ? 1 : 0); }
                 lay.xb_off = xo;
                 lay.stage_off = so;
                 lay.tw_off = two;
