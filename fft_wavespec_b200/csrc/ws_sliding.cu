@@ -722,12 +722,16 @@ static bool pick_plan(const Params& p, Plan& pl, SlideLayout& lay) {
             total = two + (p.N / 4) * 16 + 16;           // + the mbarrier of the bulk staging
             if (total <= 113 * 1024) {                   // keep two CTAs per SM
                 lay.overlap = 1;
-                // Measured (ms per 1.2 M windows, never / always / last groups only): N = 512 1.25 / 1.12 /
-                // 1.21, N = 1024 1.87 / 1.97 / 1.87.  Where the consumers are the slower side (N <= 512) the
-                // 32-bit keys pay; at N = 1024 the chains' store stream is the limit, consumers that issue
-                // faster only take issue slots from the chains, and a shorter tail buys nothing.
+                // 32-bit key selection in the consumers: 0 never, 1 always, 2 for a tile's last groups only
+                // (WAVESPEC_FASTSEL).  Measured, ms per 1.2 M windows at 1 965 MHz, never / always / last
+                // groups: N = 512 1.25 / 1.12 / 1.21, N = 1024 1.87 / 1.97 / 1.87 — at N = 1024 the chains'
+                // store stream is the limit there, and consumers that issue faster take issue slots from the
+                // chains.  But under sustained load the boxes run into their 1 kW power cap (SM clock
+                // 1 670 - 1 750 MHz), and there the 18 % fewer instructions win: bench.py 611 - 637 M spectra/s
+                // without the keys depending on the box, 634 M on every box with them (654 / 628 M for one
+                // unthrottled launch of the same shape).  Sustained load is the operating point: always on.
                 { static int fs = -1; if (fs < 0) { const char* e = getenv("WAVESPEC_FASTSEL"); fs = e ? atoi(e) : -1; }
-                  lay.fastsel = fs >= 0 ? fs : (p.N <= 512 ? 1 : 0); }
+                  lay.fastsel = fs >= 0 ? fs : 1; }
                 lay.xb_off = xo;
                 lay.stage_off = so;
                 lay.tw_off = two;
