@@ -32,13 +32,6 @@
 #include "ws_series.h"
 #include "ws_sliding_core.cuh"
 
-#ifndef WS_BULK_STAGE
-#define WS_BULK_STAGE 1
-#endif
-#ifndef WS_TW_SMEM
-#define WS_TW_SMEM 1
-#endif
-
 namespace ws {
 
 using ws_slide::Plan;
@@ -308,12 +301,13 @@ sliding_overlap_kernel(const Params p, const Plan pl, const SlideLayout lay) {
     // memory system again — a global load issued under the other CTAs' spectrum stores takes
     // thousands of cycles, and there were five of them in a row between here and the top pass.
     double2* tws = reinterpret_cast<double2*>(smem_raw + lay.tw_off);
-    const double2* twu = WS_TW_SMEM ? tws : p.tw;
+    const double2* twu = tws;
     if (p.prefetch_tiles > 0)
         prefetch_future_tile(src, p.series_len, w0 + (int64_t)p.prefetch_tiles * pl.T + (N - 1), pl.T, tid);
-#if WS_BULK_STAGE
-    // The tile and the twiddles arrive through the bulk-copy engine (cp.async.bulk + mbarrier): an
-    // ld.global issued here would queue behind the spectrum stores the SM's other CTA has in flight.
+    // The tile and the twiddles arrive through the bulk-copy engine (cp.async.bulk + mbarrier, SASS
+    // UBLKCP): one issuing thread instead of 256 threads' LDG + STS.  (Measured equal in time to plain
+    // 128-bit loads that are all in flight before the first store — the ~4 000 cycles are an L2 round
+    // trip under the chip-wide store stream, whatever path asks for it.)
     // The engine needs 16-byte aligned addresses and sizes: the sample array is shifted by one slot when
     // the tile starts on an odd sample, the copy may take one sample past the tile when the series has
     // it, and whatever is left at either end (odd first sample, end of the series) moves by plain loads.
@@ -344,20 +338,6 @@ sliding_overlap_kernel(const Params p, const Plan pl, const SlideLayout lay) {
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
                          : "=r"(done) : "r"(bar) : "memory");
     }
-#else
-    {
-        double2 twv[(N / 4 + kSlideThreads - 1) / kSlideThreads];
-#pragma unroll
-        for (int u = 0; u < (N / 4 + kSlideThreads - 1) / kSlideThreads; u++)
-            if (WS_TW_SMEM && tid + u * kSlideThreads < N / 4) twv[u] = p.tw[tid + u * kSlideThreads];
-        const int64_t left = (int64_t)p.series_len - w0;
-        stage_samples(src + w0, pl.x_len, left > pl.x_len ? pl.x_len : (int)left, x, tid, kSlideThreads);
-#pragma unroll
-        for (int u = 0; u < (N / 4 + kSlideThreads - 1) / kSlideThreads; u++)
-            if (WS_TW_SMEM && tid + u * kSlideThreads < N / 4) tws[tid + u * kSlideThreads] = twv[u];
-    }
-    __syncthreads();
-#endif
     constexpr int NST = ws_slide::LevelsOf<N>::nst;          // the plan's top is 3 here: compile-time level structure
     ws_slide::bottom_level<NST, ws_slide::LevelsOf<N>::Lb>(tid, kSlideThreads, x, pl, twu, arena);
     __syncthreads();
