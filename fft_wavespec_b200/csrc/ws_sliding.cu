@@ -6,17 +6,21 @@
 // band-limited top-K selection and row pack (:537-568 of the latter).
 //
 // One CTA owns a tile of T consecutive windows of one series:
-//   1. the T + N - 1 samples of the tile are staged in shared memory with 128-bit loads (each
-//      sample is read from HBM once per tile);
+//   1. the T + N - 1 samples of the tile are staged in shared memory — by bulk async copy
+//      (cp.async.bulk + mbarrier) in the producer / consumer kernel, with 128-bit loads that are all
+//      issued before the first store elsewhere — together with the N/4 twiddles every pass uses
+//      (each sample is read from HBM once per tile; nothing after this step waits for memory);
 //   2. the deepest decimation level is computed directly from the samples (2..16-point DFTs);
 //   3. fused radix-8 passes (ws_sliding_core.cuh) build the level-3 vectors in shared memory,
-//      sharing every sub-transform between the overlapping windows of the tile;
+//      sharing every sub-transform between the overlapping windows of the tile (items numbered
+//      position-fastest over odd position strides: no bank conflicts, warp-uniform twiddles);
 //   4. the top pass produces the N/2 complex bins of each window in registers and streams them
 //      to HBM with 128-bit stores (a warp writes contiguous 512-byte runs); in-band bins are
 //      also captured in shared memory;
 //   5. the warps run the batched top-K epilogue (ws_epilogue.cuh: four windows per warp, eight
-//      lanes each at K <= 8) on the captured band and stream the rows out; the selection-sort
-//      rule and K > 8 take the one-warp-per-window form.  Alternatively (WAVESPEC_SPLIT=1, and
+//      lanes each at K <= 8 — a sorting / merge network on 32-bit keys with the exact (double, int)
+//      network behind it) on the captured band and stream the rows out; wide bands take one pass
+//      with per-lane register lists, the selection-sort rule and K > 8 the one-warp-per-window form.  Alternatively (WAVESPEC_SPLIT=1, and
 //      always for the tracker plane) the in-band bins go to a compact global buffer consumed by
 //      ws_rows.cu / the tracker kernel.
 //
@@ -57,7 +61,8 @@ struct SlideLayout {
     int ring_off;       // staged: S rings of `ring_slots` spectrum rows (N/2 double2 each)
     int ring_slots;
     int special_off;    // staged: [T][8] bins of the packed slot 0 (multiples of N/16)
-    int tw_off;         // overlap: the N/4 twiddles every pass of the tile uses, staged beside the samples
+    int tw_off;         // the N/4 twiddles every pass of the tile uses, staged beside the samples (0: read from global);
+                        // the producer/consumer kernel keeps the mbarrier of its bulk staging right behind them
     int fastsel;        // overlap: 32-bit key selection 0 never, 1 always, 2 for a tile's last groups only
     int total_bytes;
 };
